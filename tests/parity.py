@@ -1,0 +1,36 @@
+"""The comparison rule for SOAP distances (SURVEY.md section 7 "Hard parts").
+
+``d = sqrt(2 - 2k)`` cancels catastrophically for near-identical vectors, so two correct fp64
+evaluations that merely sum in a different order differ by ``~eps / d**2`` relative in ``d``.
+The reference itself returns 2e-8 instead of 0 (``SOAPdistanceNormalized(x, x)``) or NaN
+(``SOAPdistance(x, x)`` when rounding gives k > 1).  The rule therefore is
+
+* ``d**2`` (equivalently the kernel value ``k``) agrees to ``atol`` ABSOLUTE:
+  1e-12 for the fp64 path, 1e-6 for the fp32 / 3xTF32 path (BASELINE.json north_star);
+* ``d`` agrees to the same number RELATIVE wherever ``d >= d_rel_min`` (0.1: the
+  cancellation has eaten < 2 digits there);
+* NaNs: a NaN on either side is accepted only against NaN or against ``d**2 <= atol`` on the
+  other side (both are "k rounded to just above / just below 1").
+"""
+import numpy as np
+
+TOL = {"f64": 1e-12, "f32": 1e-6}
+
+
+def assert_distance_parity(got, want, path="f64", d_rel_min=0.1, what=""):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    tol = TOL[path]
+    gn, wn = np.isnan(got), np.isnan(want)
+    only_g, only_w = gn & ~wn, wn & ~gn
+    assert (want[only_g] ** 2 <= tol).all(), f"{what}: NaN where the oracle has a finite distance"
+    assert (got[only_w] ** 2 <= tol).all(), f"{what}: finite distance where the oracle has NaN"
+    ok = ~(gn | wn)
+    err2 = np.abs(got[ok] ** 2 - want[ok] ** 2)
+    assert err2.size == 0 or err2.max() <= tol, f"{what}: max |d^2 - d^2_ref| = {err2.max():.3e} > {tol}"
+    big = ok & (want >= d_rel_min)
+    if big.any():
+        rel = np.abs(got[big] - want[big]) / want[big]
+        assert rel.max() <= tol, f"{what}: max rel err on d>= {d_rel_min}: {rel.max():.3e} > {tol}"
+    return float(err2.max()) if err2.size else 0.0
