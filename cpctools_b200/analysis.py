@@ -1,0 +1,211 @@
+"""Mirror of the timeSOAP family of ``SOAPify.analysis`` (``src/SOAPify/analysis.py:13-203``).
+
+``timeSOAP`` / ``timeSOAPsimple`` / ``getTimeSOAPSimple`` keep the reference's signatures, shapes,
+dtypes and error messages; the work is done by the time-lag kernel of ``libsoapb200.so``
+(``csrc/timelag.cu``).  Additions that have no reference counterpart are marked as such:
+``timeSOAPsweep`` (several windows in one pass), ``timeSOAPfromCompressed`` (expansion and
+normalisation folded into the distance) and the north-star alias ``tempoSOAP``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _device, _lib
+from .distances import resolve_distance, simpleSOAPdistance
+from .utils import getExpansionPlan, getSOAPSettings, orderByZ, _quippyContainerSlices
+
+__all__ = [
+    "timeSOAP",
+    "tempoSOAP",
+    "timeSOAPsimple",
+    "getTimeSOAPSimple",
+    "timeSOAPsweep",
+    "timeSOAPfromCompressed",
+]
+
+
+def _validate(n_frames: int, window: int, stride):
+    # analysis.py:47-52 (messages pinned by the reference's tests/test_analysis.py:41,46)
+    if stride is None:
+        stride = window
+    if stride > window:
+        raise ValueError("the window must be bigger than the stride")
+    if window >= n_frames or stride >= n_frames:
+        raise ValueError("stride and window must be smaller than simulation lenght")
+    if window < 1:
+        raise ValueError("the window must be at least 1")
+
+
+def timelag_device(X, windows, kind: int, power: int = 1, mult=None):
+    """Run the time-lag kernel on a CUDA tensor ``X[F, A, D]``; returns one ``[F-w, A]`` float64
+    CUDA tensor per window (all windows of a group of <= 4 share ONE pass over ``X``)."""
+    th = _device.require_cuda()
+    lib = _lib.load()
+    if X.dim() != 3:
+        raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
+    F, A, D = (int(s) for s in X.shape)
+    windows = [int(w) for w in windows]
+    results = {}
+    todo = sorted(set(windows))
+    for g in range(0, len(todo), _lib.MAX_WINDOWS):
+        group = todo[g : g + _lib.MAX_WINDOWS]
+        nw = len(group)
+        sizes = [(F - w) * A for w in group]
+        offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        t = th.empty(int(sum(sizes)), dtype=th.float64, device=X.device)
+        c_w = (ctypes.c_int * nw)(*group)
+        c_off = (ctypes.c_int64 * nw)(*[int(o) for o in offsets])
+        code = _device.dtype_code(X)
+        nbytes = lib.soap_timelag_scratch_bytes(F, A, D, code, c_w, nw)
+        if nbytes == 0:
+            raise _lib.SoapB200Error(f"timeSOAP: window {max(group)} does not fit the shared-memory ring")
+        scratch = th.empty(nbytes // 8, dtype=th.float64, device=X.device)
+        rc = lib.soap_timelag(
+            X.data_ptr(), None if mult is None else mult.data_ptr(), t.data_ptr(), c_off, F, A, D, c_w, nw,
+            kind, int(power), code, scratch.data_ptr(), _device.stream_ptr(),
+        )
+        _lib.check(rc, "soap_timelag")
+        for w, o, n in zip(group, offsets, sizes):
+            results[w] = t[int(o) : int(o) + n].view(F - w, A)
+    return [results[w] for w in windows]
+
+
+def diff_transposed_device(t):
+    """``numpy.diff(t.T, axis=-1)`` on the device: ``[rows, A] -> [A, rows-1]`` (analysis.py:67)."""
+    th = _device.require_cuda()
+    rows, A = (int(s) for s in t.shape)
+    dt = th.empty((A, max(rows - 1, 0)), dtype=th.float64, device=t.device)
+    if rows > 1 and A > 0:
+        rc = _lib.load().soap_diff_transposed(t.data_ptr(), dt.data_ptr(), rows, A, _device.stream_ptr())
+        _lib.check(rc, "soap_diff_transposed")
+    return dt
+
+
+def _finish(t, like, returnDiff):
+    if returnDiff:
+        return _device.like_input(t, like), _device.like_input(diff_transposed_device(t), like)
+    return _device.like_input(t, like)
+
+
+def timeSOAP(
+    SOAPTrajectory,
+    window: int = 1,
+    stride: int = None,
+    backward: bool = False,
+    returnDiff: bool = True,
+    distanceFunction: callable = simpleSOAPdistance,
+):
+    """performs the 'timeSOAP' analysis on the given SOAP trajectory (analysis.py:13-69).
+
+    ``t[f-window, a] = distanceFunction(X[f, a], X[f-window, a])``; returns ``t`` (float64,
+    ``(frames-window, natoms)``) and, if ``returnDiff``, ``numpy.diff(t.T, axis=-1)``.  ``stride`` and
+    ``backward`` are validated but unused, as in the reference.  ``distanceFunction`` must be one of
+    the built-in distances of :mod:`cpctools_b200.distances` (dispatched by identity).
+    """
+    _validate(int(SOAPTrajectory.shape[0]), window, stride)
+    kind, power = resolve_distance(distanceFunction)
+    X = _device.as_float_tensor(SOAPTrajectory)
+    (t,) = timelag_device(X, [window], kind, power)
+    return _finish(t, SOAPTrajectory, returnDiff)
+
+
+def tempoSOAP(*args, **kwargs):
+    """Historical name of :func:`timeSOAP` (reference ``Changelog.md:51``); north-star alias."""
+    return timeSOAP(*args, **kwargs)
+
+
+def timeSOAPsweep(SOAPTrajectory, windows=(1, 5, 10, 50), returnDiff: bool = True, distanceFunction: callable = simpleSOAPdistance):
+    """``[timeSOAP(X, window=w, ...) for w in windows]`` with ONE pass over ``X`` per group of four
+    windows (no reference counterpart: the reference would be called once per window)."""
+    n_frames = int(SOAPTrajectory.shape[0])
+    for w in windows:
+        _validate(n_frames, int(w), None)
+    kind, power = resolve_distance(distanceFunction)
+    X = _device.as_float_tensor(SOAPTrajectory)
+    return [_finish(t, SOAPTrajectory, returnDiff) for t in timelag_device(X, windows, kind, power)]
+
+
+def timeSOAPfromCompressed(
+    soapFromdscribe,
+    lMax: int,
+    nMax: int,
+    atomTypes: list = None,
+    atomicSlices: dict = None,
+    windows=(1,),
+    returnDiff: bool = True,
+    distanceFunction: callable = simpleSOAPdistance,
+    quippy: bool = False,
+):
+    """``timeSOAP(normalizeArray(fillSOAPVectorFromdscribe(x, ...)), window=w)`` for every ``w`` in
+    ``windows`` WITHOUT materialising the expanded vectors: the dot products of the expanded
+    vectors are multiplicity-weighted dot products of the compressed ones, and the cosine-type
+    distances do not depend on the normalisation (``SOAPdistanceNormalized`` divides by the norms,
+    zero norm -> 1, exactly as ``normalizeArray`` would have).  Reads ``Dc`` instead of ``Df``
+    elements per vector.  ``quippy=True`` takes RAW quippy rows (``[..., Dc+1]``).
+    """
+    if quippy:
+        species = orderByZ([str(s) for s in atomTypes])
+        plan = getExpansionPlan(lMax, nMax, species, atomicSlices or _quippyContainerSlices(lMax, nMax, species), quippy=True)
+    else:
+        plan = getExpansionPlan(lMax, nMax, atomTypes, atomicSlices)
+    if soapFromdscribe.shape[-1] != plan.d_compressed:
+        raise ValueError("fillSOAPVectorFromdscribe: the given soap vector do not have the expected dimensions")
+    n_frames = int(soapFromdscribe.shape[0])
+    for w in windows:
+        _validate(n_frames, int(w), None)
+    kind, power = resolve_distance(distanceFunction)
+    if kind == _lib.KIND_NORMALIZED:
+        kind = _lib.KIND_NORMALIZED_FUSED
+    X = _device.as_float_tensor(soapFromdscribe)
+    mult = plan.multiplicity_device(X.dtype)
+    return [
+        _finish(t, soapFromdscribe, returnDiff) for t in timelag_device(X, windows, kind, power, mult=mult)
+    ]
+
+
+def _simple_rows(X, window: int):
+    """Rows of ``timeSOAPsimple`` on a CUDA tensor: the reference's ``prev`` trails by ONE frame
+    (analysis.py:132-137), so row 0 is ``|X[w] - X[0]|`` and row r >= 1 is ``|X[w+r] - X[w+r-1]|``."""
+    th = _device.require_cuda()
+    F = int(X.shape[0])
+    if window == 1:
+        return timelag_device(X, [1], _lib.KIND_EUCLID)[0]
+    lag1, lagw = timelag_device(X, [1, window], _lib.KIND_EUCLID)
+    t = th.empty((F - window, int(X.shape[1])), dtype=th.float64, device=X.device)
+    t[0] = lagw[0]
+    if F - window > 1:
+        t[1:] = lag1[window:]
+    return t
+
+
+def timeSOAPsimple(SOAPTrajectory, window: int = 1, stride: int = None, backward: bool = False, returnDiff: bool = True):
+    """performs the 'timeSOAP' analysis on the given **normalized** SOAP trajectory (analysis.py:72-142).
+
+    Euclidean distance between consecutive frames' versors.  Kept literally, including the
+    reference's behaviour for ``window > 1`` (only row 0 spans ``window`` frames, see
+    :func:`_simple_rows`); use :func:`timeSOAP` for true lag-``window`` distances.
+    """
+    _validate(int(SOAPTrajectory.shape[0]), window, stride)
+    X = _device.as_float_tensor(SOAPTrajectory)
+    return _finish(_simple_rows(X, int(window)), SOAPTrajectory, returnDiff)
+
+
+def getTimeSOAPSimple(soapDataset, window: int = 1, stride: int = None, backward: bool = False):
+    """Shortcut to extract the timeSOAP from large datasets (analysis.py:145-203).
+
+    Streams the dataset chunk by chunk (``iter_chunks()``), each chunk going pinned host buffer ->
+    HBM -> fused expand+normalise kernel -> Euclidean time-lag kernel, with the last ``window``
+    frames of a chunk kept ON THE DEVICE as the halo of the next one (the reference re-reads one
+    frame from HDF5).  ``window == 1`` reproduces the reference; for ``window > 1`` the reference
+    raises a broadcast ``ValueError`` while this returns the true
+    lag-``window`` distances.  Returns ``(t[F-window, A], numpy.diff(t.T, axis=-1))`` as numpy arrays.
+    """
+    from .streaming import stream_time_soap
+
+    n_frames = int(soapDataset.shape[0])
+    _validate(n_frames, window, stride)
+    settings = getSOAPSettings(soapDataset)
+    (t,) = stream_time_soap(soapDataset, settings, [int(window)], euclid=True)
+    return _device.to_host(t), _device.to_host(diff_transposed_device(t))

@@ -1,0 +1,220 @@
+"""Mirror of the distance-matrix / classification part of ``SOAPify.classify``
+(``src/SOAPify/classify.py:17-48, 51-93, 96-182, 185-205, 250-276``).
+
+``getDistanceBetween`` is the all-pairs boundary (``getDistanceBetween(X, X, f)``); the
+``getDistancesFromRef*`` / ``applyClassification`` functions stream a chunked dataset through
+expand -> normalise -> distance-to-references (-> fused argmin) on the GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable
+
+import numpy as np
+
+from . import _device, _lib
+from .distances import SOAPdistanceNormalized, resolve_distance
+from .streaming import _Uploader, frame_ranges
+from .utils import fillSOAPVectorFromdscribe, getExpansionPlan, normalizeArray
+
+__all__ = [
+    "SOAPclassification",
+    "SOAPReferences",
+    "createReferencesFromTrajectory",
+    "getDistanceBetween",
+    "getDistancesFromRef",
+    "getDistancesFromRefNormalized",
+    "getDistancesFromInterval",
+    "mergeReferences",
+    "applyClassification",
+]
+
+
+@dataclass
+class SOAPclassification:
+    """Stores the information about the SOAP classification of a trajectory (classify.py:17-29)."""
+
+    distances: "np.ndarray[float]"  #: per frame, per atom distance from the closest reference
+    references: "np.ndarray[int]"  #: per frame, per atom index of the closest reference
+    legend: "list[str]"  #: the references legend
+
+
+@dataclass
+class SOAPReferences:
+    """Stores the spectra selected for an environments dictionary (classify.py:31-48)."""
+
+    names: "list[str]"
+    spectra: "np.ndarray[np.float64]"
+    lmax: int
+    nmax: int
+
+    def __len__(self) -> int:
+        return len(self.names)
+
+
+def createReferencesFromTrajectory(h5SOAPDataSet, addresses: dict, lmax: int, nmax: int, doNormalize=True) -> SOAPReferences:
+    """Pick ``dataset[frame, atom]`` fingerprints as references (classify.py:51-93).  Expansion and
+    normalisation of the picked vectors run on the GPU.  The reference compares the stored
+    dimension with ``lmax*nmax*nmax`` (not ``(lmax+1)``, classify.py:85) to decide whether to expand;
+    that test is kept as is."""
+    names = list(addresses.keys())
+    dim = h5SOAPDataSet.shape[2]
+    spectra = np.empty((len(addresses), dim), dtype=h5SOAPDataSet.dtype)
+    for i, key in enumerate(addresses):
+        spectra[i] = h5SOAPDataSet[addresses[key][0], addresses[key][1]]
+    if lmax * nmax * nmax != dim:
+        spectra = fillSOAPVectorFromdscribe(spectra, lmax, nmax)
+    if doNormalize:
+        spectra = normalizeArray(spectra)
+    return SOAPReferences(names, spectra, lmax, nmax)
+
+
+def mergeReferences(*x: SOAPReferences) -> SOAPReferences:
+    """Concatenate reference dictionaries (classify.py:185-205)."""
+    names = []
+    for i in x:
+        names += i.names
+        if x[0].nmax != i.nmax or x[0].lmax != i.lmax:
+            raise ValueError("nmax or lmax are not the same in the two references")
+    return SOAPReferences(names, np.concatenate([i.spectra for i in x]), nmax=x[0].nmax, lmax=x[0].lmax)
+
+
+def pairs_device(data, spectra, kind: int, power: int = 1, path: int = _lib.PAIRS_AUTO, out=None, want_argmin=False):
+    """Distance matrix of two CUDA tensors ``[M, D]`` x ``[K, D]`` (same float dtype).
+
+    Returns the ``[M, K]`` matrix, or ``(min float64[M], argmin int32[M])`` when ``want_argmin``."""
+    th = _device.require_cuda()
+    lib = _lib.load()
+    M, D = (int(s) for s in data.shape)
+    K = int(spectra.shape[0])
+    if int(spectra.shape[1]) != D:
+        raise ValueError("shapes not aligned")
+    code = _device.dtype_code(data)
+    stream = _device.stream_ptr()
+    if want_argmin:
+        amin = th.empty(M, dtype=th.float64, device=data.device)
+        arg = th.empty(M, dtype=th.int32, device=data.device)
+        if M and K:
+            rc = lib.soap_pairs(data.data_ptr(), spectra.data_ptr(), None, M, K, D, K, kind, int(power), code,
+                                _lib.PAIRS_SIMT, arg.data_ptr(), amin.data_ptr(), None, stream)
+            _lib.check(rc, "soap_pairs")
+        return amin, arg
+    if out is None:
+        out = th.empty((M, K), dtype=data.dtype, device=data.device)
+    if M and K:
+        scratch = None
+        if path != _lib.PAIRS_SIMT:
+            nbytes = lib.soap_pairs_scratch_bytes(M, K, D, code, path)
+            scratch = th.empty(max(int(nbytes), 8), dtype=th.uint8, device=data.device)
+        rc = lib.soap_pairs(data.data_ptr(), spectra.data_ptr(), out.data_ptr(), M, K, D, int(out.stride(0)), kind,
+                            int(power), code, path, None, None, None if scratch is None else scratch.data_ptr(), stream)
+        _lib.check(rc, "soap_pairs")
+    return out
+
+
+def getDistanceBetween(data, spectra, distanceCalculator: Callable):
+    """Array of the distances between ``data`` and ``spectra`` (classify.py:96-117).
+
+    ``out[i, j] = distanceCalculator(data[i], spectra[j])``, shape ``(len(data), len(spectra))``,
+    dtype ``data.dtype``.  ``getDistanceBetween(X, X, f)`` is the all-pairs SOAP distance matrix
+    (tensor-core GEMM with the distance as its epilogue when the matrix is large)."""
+    kind, power = resolve_distance(distanceCalculator)
+    th = _device.require_cuda()
+    a = _device.as_float_tensor(data)
+    b = _device.as_float_tensor(spectra)
+    if a.dtype != b.dtype:
+        b = b.to(a.dtype)
+    out = pairs_device(a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1), kind, power)
+    if _device.is_tensor(data):
+        return out
+    res = _device.to_host(out)
+    want = np.asarray(data).dtype
+    return res if res.dtype == want else res.astype(want)  # classify.py:113: zeros(..., dtype=data.dtype)
+
+
+def _prepared_blocks(SOAPTrajData, references: SOAPReferences, doNormalize: bool, frames: slice = None):
+    """Yield ``(lo, hi, rows)``: the frames ``lo:hi`` of the dataset as a CUDA tensor
+    ``[(hi-lo)*A, D]``, expanded (mono-species signature, classify.py:151) and normalised as asked."""
+    th = _device.require_cuda()
+    lib = _lib.load()
+    F, A = int(SOAPTrajData.shape[0]), int(SOAPTrajData.shape[1])
+    first, last, _ = (frames or slice(None)).indices(F)
+    Dref = int(np.asarray(references.spectra).shape[-1])
+    Dc = int(SOAPTrajData.shape[-1])
+    convert = Dc != Dref
+    plan = getExpansionPlan(references.lmax, references.nmax) if convert else None
+    if convert and plan.d_compressed != Dc:
+        raise ValueError("fillSOAPVectorFromdscribe: the given soap vector do not have the expected dimensions")
+    budget_frames = max(1, (4 << 30) // max(1, A * max(Dc, Dref) * 8))
+    up = _Uploader(th)
+    for lo, hi in frame_ranges(SOAPTrajData, budget_frames):
+        lo, hi = max(lo, first), min(hi, last)
+        if lo >= hi:
+            continue
+        host = np.asarray(SOAPTrajData[lo:hi])
+        if host.dtype not in (np.float32, np.float64):
+            host = host.astype(np.float64)
+        raw = up.put(host)
+        rows = raw.reshape(-1, Dc)
+        if convert or doNormalize:
+            out = th.empty((rows.shape[0], Dref), dtype=rows.dtype, device="cuda")
+            if doNormalize:
+                rc = lib.soap_expand_normalize(rows.data_ptr(), out.data_ptr(),
+                                               plan.index_device().data_ptr() if convert else None,
+                                               rows.shape[0], Dc, Dref, _device.dtype_code(rows), _device.stream_ptr())
+            else:
+                rc = lib.soap_expand(rows.data_ptr(), out.data_ptr(), plan.index_device().data_ptr(), rows.shape[0],
+                                     Dc, Dref, rows.element_size(), _device.stream_ptr())
+            _lib.check(rc, "expand")
+            rows = out
+        yield lo, hi, rows
+
+
+def getDistancesFromRef(SOAPTrajData, references: SOAPReferences, distanceCalculator: Callable, doNormalize: bool = False):
+    """Distances between a SOAP-hdf5 trajectory and the given references (classify.py:120-160):
+    ``float64[F, A, len(references)]`` (numpy)."""
+    return getDistancesFromInterval(SOAPTrajData, references, distanceCalculator, doNormalize)
+
+
+def getDistancesFromInterval(SOAPTrajData, references: SOAPReferences, distanceCalculator: Callable,
+                             doNormalize: bool = False, interval: slice = None):
+    """:func:`getDistancesFromRef` restricted to the frames ``interval`` (default: all).  North-star
+    name with no reference symbol; same arithmetic as classify.py:120-160."""
+    kind, power = resolve_distance(distanceCalculator)
+    th = _device.require_cuda()
+    F, A = int(SOAPTrajData.shape[0]), int(SOAPTrajData.shape[1])
+    first, last, _ = (interval or slice(None)).indices(F)
+    K = len(references)
+    result = np.zeros((max(last - first, 0), A, K))
+    refs = None
+    for lo, hi, rows in _prepared_blocks(SOAPTrajData, references, doNormalize, interval):
+        if refs is None or refs.dtype != rows.dtype:
+            refs = _device.to_device(np.asarray(references.spectra), dtype=rows.dtype)
+        d = pairs_device(rows, refs, kind, power)
+        result[lo - first : hi - first] = _device.to_host(d.to(th.float64)).reshape(hi - lo, A, K)
+    return result
+
+
+def getDistancesFromRefNormalized(SOAPTrajData, references: SOAPReferences):
+    """Shortcut for :func:`getDistancesFromRef` forcing normalisation (classify.py:163-182)."""
+    return getDistancesFromRef(SOAPTrajData, references, SOAPdistanceNormalized, doNormalize=True)
+
+
+def applyClassification(SOAPTrajData, references: SOAPReferences, distanceCalculator: Callable, doNormalize: bool = False) -> SOAPclassification:
+    """Classify every atom of every frame by its closest reference (classify.py:250-276).
+
+    The ``[F, A, K]`` distance array is never materialised: the pair kernel keeps the running
+    ``amin`` / ``argmin`` per row (numpy's NaN and tie rules)."""
+    kind, power = resolve_distance(distanceCalculator)
+    th = _device.require_cuda()
+    F, A = int(SOAPTrajData.shape[0]), int(SOAPTrajData.shape[1])
+    dist = np.zeros((F, A))
+    ids = np.zeros((F, A), dtype=np.int64)
+    refs = None
+    for lo, hi, rows in _prepared_blocks(SOAPTrajData, references, doNormalize):
+        if refs is None or refs.dtype != rows.dtype:
+            refs = _device.to_device(np.asarray(references.spectra), dtype=rows.dtype)
+        amin, arg = pairs_device(rows, refs, kind, power, want_argmin=True)
+        dist[lo:hi] = _device.to_host(amin).reshape(hi - lo, A)
+        ids[lo:hi] = _device.to_host(arg).reshape(hi - lo, A)
+    return SOAPclassification(dist, ids, references.names)

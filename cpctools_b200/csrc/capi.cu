@@ -1,0 +1,139 @@
+// capi.cu -- error plumbing, device queries and the synthetic-data generator of libsoapb200.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+#include <mutex>
+#include <vector>
+
+namespace soapb {
+
+std::atomic<int64_t> g_launches{0};
+
+std::string &last_error() {
+  static thread_local std::string msg;
+  return msg;
+}
+
+int set_error(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SOAP_ECUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return SOAP_OK;
+}
+
+static int query_attr(cudaDeviceAttr attr, int dflt) {
+  int dev = 0, val = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return dflt;
+  if (cudaDeviceGetAttribute(&val, attr, dev) != cudaSuccess) return dflt;
+  return val;
+}
+int num_sms() { return query_attr(cudaDevAttrMultiProcessorCount, 148); }
+int max_smem_optin() { return query_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, 232448); }
+
+// ---- profiling hook ------------------------------------------------------------------------
+struct ProfRec {
+  int id;
+  cudaEvent_t start, stop;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec *> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+ProfScope::ProfScope(int kernel_id, cudaStream_t s) : id(kernel_id), stream(s), rec(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  auto *r = new ProfRec{kernel_id, nullptr, nullptr};
+  if (cudaEventCreate(&r->start) != cudaSuccess || cudaEventCreate(&r->stop) != cudaSuccess) {
+    delete r;
+    return;
+  }
+  cudaEventRecord(r->start, stream);
+  rec = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec) return;
+  auto *r = static_cast<ProfRec *>(rec);
+  cudaEventRecord(r->stop, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
+
+// splitmix64 finaliser on (seed, index): cheap, stateless, reproducible on the host
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void fill_uniform_kernel(T *out, long long n, uint64_t seed) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t r = mix64(seed * 0xD1342543DE82EF95ull + (uint64_t)i);
+    if (sizeof(T) == 8)
+      out[i] = (T)((double)(r >> 11) * (1.0 / 9007199254740992.0));
+    else
+      out[i] = (T)((float)(r >> 40) * (1.0f / 16777216.0f));
+  }
+}
+
+}  // namespace soapb
+
+using namespace soapb;
+
+extern "C" int soap_abi_version(void) { return SOAP_B200_ABI_VERSION; }
+extern "C" const char *soap_last_error(void) { return last_error().c_str(); }
+extern "C" int64_t soap_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int soap_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto *r : g_prof) {
+    cudaEventDestroy(r->start);
+    cudaEventDestroy(r->stop);
+    delete r;
+  }
+  g_prof.clear();
+  g_prof_on.store(on ? 1 : 0);
+  return SOAP_OK;
+}
+
+extern "C" int soap_profile_read(int kernel_id, float *ms_out_host, int capacity) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (auto *r : g_prof) {
+    if (r->id != kernel_id) continue;
+    if (cudaEventSynchronize(r->stop) != cudaSuccess) return set_error(SOAP_ECUDA, "soap_profile_read: event sync failed");
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r->start, r->stop) != cudaSuccess)
+      return set_error(SOAP_ECUDA, "soap_profile_read: elapsed time failed");
+    if (ms_out_host && n < capacity) ms_out_host[n] = ms;
+    ++n;
+  }
+  return n;
+}
+
+extern "C" int soap_fill_uniform(void *out, int64_t n, uint64_t seed, int dtype, void *stream) {
+  SOAP_REQUIRE(n >= 0, "soap_fill_uniform: negative size");
+  if (n == 0) return SOAP_OK;
+  SOAP_REQUIRE(out != nullptr, "soap_fill_uniform: null buffer");
+  auto s = static_cast<cudaStream_t>(stream);
+  const int grid = num_sms() * 8;
+  if (dtype == SOAP_F64)
+    fill_uniform_kernel<double><<<grid, 256, 0, s>>>(static_cast<double *>(out), (long long)n, seed);
+  else if (dtype == SOAP_F32)
+    fill_uniform_kernel<float><<<grid, 256, 0, s>>>(static_cast<float *>(out), (long long)n, seed);
+  else
+    return set_error(SOAP_EUNSUPPORTED, "soap_fill_uniform: dtype %d", dtype);
+  return check_launch("fill_uniform_kernel");
+}

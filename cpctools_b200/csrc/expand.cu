@@ -1,0 +1,220 @@
+// expand.cu -- K1/K2: gather-expand of compressed SOAP power spectra, optionally fused with
+// the L2 normalisation of the expanded vector.
+//
+// Reference semantics: fillSOAPVectorFromdscribe (src/SOAPify/utils.py:271-324: x[..., idx]) and
+// normalizeArray (utils.py:140-153: x / norm, zero-norm rows left at zero).
+//
+// Memory-bound (reads Dc, writes Df elements per vector).  One CTA owns a tile of TV
+// consecutive vectors -- contiguous in memory -- which the TMA engine drops into shared
+// memory with ONE 1-D bulk copy (cp.async.bulk, double buffered, mbarrier completion); the
+// gather then runs out of shared memory and leaves as fully coalesced 128-bit streaming stores.
+// The int32 gather table lives in shared memory and is hoisted into registers per column chunk.
+#include "common.cuh"
+
+namespace soapb {
+
+template <typename T>
+struct VecOf;  // 16-byte vector of T
+template <>
+struct VecOf<double> { static constexpr int N = 2; };
+template <>
+struct VecOf<float> { static constexpr int N = 4; };
+template <>
+struct VecOf<uint64_t> { static constexpr int N = 2; };
+template <>
+struct VecOf<uint32_t> { static constexpr int N = 4; };
+
+constexpr int kExpandThreads = 256;
+
+template <typename T>
+__device__ __forceinline__ T scale_elem(T v, double nrm) {
+  return v;
+}
+// IEEE division in the data's own precision, as numpy does for x / norm
+template <>
+__device__ __forceinline__ double scale_elem<double>(double v, double nrm) {
+  return v / nrm;
+}
+template <>
+__device__ __forceinline__ float scale_elem<float>(float v, double nrm) {
+  return v / (float)nrm;
+}
+
+template <typename T>
+__device__ __forceinline__ double sq_as_double(T v) {
+  return 0.0;
+}
+template <>
+__device__ __forceinline__ double sq_as_double<double>(double v) {
+  return v * v;
+}
+template <>
+__device__ __forceinline__ double sq_as_double<float>(float v) {
+  return (double)v * (double)v;
+}
+
+// T: element type; NORM: fuse normalisation; HAS_IDX: gather table present (else identity)
+template <typename T, bool NORM, bool HAS_IDX>
+__global__ void __launch_bounds__(kExpandThreads, 2)
+    expand_kernel(const T *__restrict__ in, T *__restrict__ out, const int32_t *__restrict__ idx,
+                  long long nvec, int in_stride, int d_full, int tv, int bulk_ok, int vec_ok) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int V = VecOf<T>::N;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kExpandThreads / 32;
+
+  const size_t stage_elems = (size_t)tv * in_stride;
+  const size_t stage_bytes = ((stage_elems * sizeof(T)) + 127) & ~(size_t)127;
+  T *stage[2] = {reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + stage_bytes)};
+  int32_t *tab = reinterpret_cast<int32_t *>(smem_raw + 2 * stage_bytes);
+  const int d_pad = (d_full + 3) & ~3;
+  double *nrm = reinterpret_cast<double *>(tab + (HAS_IDX ? d_pad : 0));
+  uint64_t *bar = reinterpret_cast<uint64_t *>(nrm + ((tv + 1) & ~1));
+
+  const long long ntiles = (nvec + tv - 1) / tv;
+  if (HAS_IDX) {
+    for (int j = tid; j < d_pad; j += kExpandThreads) tab[j] = (j < d_full) ? idx[j] : 0;
+  }
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto tile_rows = [&](long long t) -> int {
+    long long left = nvec - t * tv;
+    return (int)(left < tv ? left : tv);
+  };
+  auto issue = [&](long long t, int s) {  // thread 0 only, bulk path
+    const uint32_t bytes = (uint32_t)((size_t)tile_rows(t) * in_stride * sizeof(T));
+    mbar_expect_tx(&bar[s], bytes);
+    bulk_g2s(stage[s], in + (size_t)t * tv * in_stride, bytes, &bar[s]);
+  };
+
+  long long t = blockIdx.x;
+  int s = 0;
+  uint32_t phase[2] = {0, 0};
+  if (bulk_ok && tid == 0 && t < ntiles) issue(t, 0);
+
+  for (; t < ntiles; t += gridDim.x, s ^= 1) {
+    const int rows = tile_rows(t);
+    if (bulk_ok) {
+      const long long tn = t + gridDim.x;
+      // stage s^1 was last read in the previous iteration (trailing __syncthreads below)
+      if (tid == 0 && tn < ntiles) issue(tn, s ^ 1);
+      mbar_wait(&bar[s], phase[s]);
+      phase[s] ^= 1;
+    } else {
+      const T *src = in + (size_t)t * tv * in_stride;
+      const int n = rows * in_stride;
+      for (int i = tid; i < n; i += kExpandThreads) stage[s][i] = src[i];
+      __syncthreads();
+    }
+    const T *sm = stage[s];
+
+    if (NORM) {
+      // phase 1: one warp per vector, squared norm of the EXPANDED vector in double
+      for (int v = warp; v < rows; v += kWarps) {
+        const T *row = sm + (size_t)v * in_stride;
+        double acc = 0.0;
+        for (int j = lane; j < d_full; j += 32) acc += sq_as_double<T>(row[HAS_IDX ? tab[j] : j]);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          double r = sqrt(acc);
+          nrm[v] = (r == 0.0) ? 1.0 : r;
+        }
+      }
+      __syncthreads();
+    }
+
+    // phase 2: gather (+ scale) and stream out
+    T *dst = out + (size_t)t * tv * d_full;
+    if (vec_ok) {
+      const int nchunk = d_full / V;  // d_full % V == 0 when vec_ok
+      for (int c = tid; c < nchunk; c += kExpandThreads) {
+        int col[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) col[k] = HAS_IDX ? tab[c * V + k] : (c * V + k);
+#pragma unroll 4
+        for (int v = 0; v < rows; ++v) {
+          const T *row = sm + (size_t)v * in_stride;
+          union {
+            int4 q;
+            T e[V];
+          } u;
+          const double nv = NORM ? nrm[v] : 1.0;
+#pragma unroll
+          for (int k = 0; k < V; ++k) u.e[k] = NORM ? scale_elem<T>(row[col[k]], nv) : row[col[k]];
+          stg_stream16(dst + (size_t)v * d_full + (size_t)c * V, u.q);
+        }
+      }
+    } else {
+      const int total = rows * d_full;
+      for (int q = tid; q < total; q += kExpandThreads) {
+        const int v = q / d_full, j = q - v * d_full;
+        const T val = sm[(size_t)v * in_stride + (HAS_IDX ? tab[j] : j)];
+        dst[q] = NORM ? scale_elem<T>(val, nrm[v]) : val;
+      }
+    }
+    __syncthreads();  // everyone is done with stage s (and nrm) before it is refilled
+  }
+}
+
+template <typename T, bool NORM>
+static int launch_expand(const void *in, void *out, const int32_t *idx, int64_t nvec,
+                         int in_stride, int d_full, cudaStream_t stream) {
+  if (nvec == 0) return SOAP_OK;
+  const size_t row_bytes = (size_t)in_stride * sizeof(T);
+  // tile of ~40 KB per stage so that two CTAs (4 stages) fit in one SM's shared memory
+  int tv = (int)(40960 / row_bytes);
+  if (tv < 1) tv = 1;
+  if (tv > 64) tv = 64;
+  if ((int64_t)tv > nvec) tv = (int)nvec;
+  const size_t stage_bytes = (((size_t)tv * row_bytes) + 127) & ~(size_t)127;
+  const int d_pad = (d_full + 3) & ~3;
+  const size_t smem = 2 * stage_bytes + (idx ? (size_t)d_pad * 4 : 0) + ((tv + 1) & ~1) * 8 + 16;
+  if (smem > (size_t)max_smem_optin())
+    return set_error(SOAP_EUNSUPPORTED, "soap_expand: a single vector of %zu bytes does not fit in shared memory",
+                     row_bytes);
+  const int bulk_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (row_bytes % 16 == 0);
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                     (((size_t)d_full * sizeof(T)) % 16 == 0);
+  const int64_t ntiles = (nvec + tv - 1) / tv;
+  const int per_sm = smem * 2 <= (size_t)max_smem_optin() ? 2 : 1;
+  int grid = (int)(ntiles < (int64_t)num_sms() * per_sm ? ntiles : (int64_t)num_sms() * per_sm);
+  auto kern = idx ? expand_kernel<T, NORM, true> : expand_kernel<T, NORM, false>;
+  SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(SOAP_PROF_EXPAND, stream);
+  kern<<<grid, kExpandThreads, smem, stream>>>(static_cast<const T *>(in), static_cast<T *>(out), idx,
+                                                (long long)nvec, in_stride, d_full, tv, bulk_ok, vec_ok);
+  return check_launch("expand_kernel");
+}
+
+}  // namespace soapb
+
+using namespace soapb;
+
+extern "C" int soap_expand(const void *in, void *out, const int32_t *idx, int64_t nvec,
+                           int in_row_stride, int d_full, int elem_size, void *stream) {
+  SOAP_REQUIRE(nvec >= 0 && in_row_stride > 0 && d_full > 0, "soap_expand: bad shape");
+  SOAP_REQUIRE(nvec == 0 || (in && out), "soap_expand: null buffer");
+  SOAP_REQUIRE(idx != nullptr, "soap_expand: idx table is required");
+  auto s = static_cast<cudaStream_t>(stream);
+  if (elem_size == 8) return launch_expand<uint64_t, false>(in, out, idx, nvec, in_row_stride, d_full, s);
+  if (elem_size == 4) return launch_expand<uint32_t, false>(in, out, idx, nvec, in_row_stride, d_full, s);
+  return set_error(SOAP_EUNSUPPORTED, "soap_expand: element size %d (only 4 and 8 bytes)", elem_size);
+}
+
+extern "C" int soap_expand_normalize(const void *in, void *out, const int32_t *idx, int64_t nvec,
+                                     int in_row_stride, int d_full, int dtype, void *stream) {
+  SOAP_REQUIRE(nvec >= 0 && in_row_stride > 0 && d_full > 0, "soap_expand_normalize: bad shape");
+  SOAP_REQUIRE(nvec == 0 || (in && out), "soap_expand_normalize: null buffer");
+  SOAP_REQUIRE(idx != nullptr || d_full == in_row_stride,
+               "soap_expand_normalize: identity table needs d_full == in_row_stride");
+  auto s = static_cast<cudaStream_t>(stream);
+  if (dtype == SOAP_F64) return launch_expand<double, true>(in, out, idx, nvec, in_row_stride, d_full, s);
+  if (dtype == SOAP_F32) return launch_expand<float, true>(in, out, idx, nvec, in_row_stride, d_full, s);
+  return set_error(SOAP_EUNSUPPORTED, "soap_expand_normalize: dtype %d", dtype);
+}

@@ -1,0 +1,102 @@
+"""Mirror of ``SOAPify.distances`` (``src/SOAPify/distances.py``): the SOAP distance family.
+
+The five functions keep the reference's names and signatures.  Called on two vectors they run
+the pair kernel on the GPU (a 1 x 1 distance matrix -- correct, but meant for spot checks: the
+throughput paths are ``timeSOAP`` / ``getDistanceBetween``, which recognise these functions BY
+IDENTITY and run the matching fused kernel instead of calling them per pair).  Any other callable
+is refused there with ``NotImplementedError``: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import functools
+
+from . import _device, _lib
+
+__all__ = [
+    "simpleKernelSoap",
+    "simpleSOAPdistance",
+    "kernelSoap",
+    "SOAPdistance",
+    "SOAPdistanceNormalized",
+    "kernelSOAPdistance",
+]
+
+
+def _pair(x, y, kind: int, power: int = 1):
+    th = _device.require_cuda()
+    lib = _lib.load()
+    a = _device.as_float_tensor(x).reshape(1, -1)
+    b = _device.as_float_tensor(y).reshape(1, -1)
+    if a.shape != b.shape:
+        raise ValueError("shapes not aligned")
+    if a.dtype != b.dtype:
+        a, b = a.to(th.float64), b.to(th.float64)
+    out = th.empty((1, 1), dtype=a.dtype, device=a.device)
+    rc = lib.soap_pairs(
+        a.data_ptr(), b.data_ptr(), out.data_ptr(), 1, 1, a.shape[1], 1, kind, int(power),
+        _device.dtype_code(a), _lib.PAIRS_SIMT, None, None, None, _device.stream_ptr(),
+    )
+    _lib.check(rc, "soap_pairs")
+    if _device.is_tensor(x):
+        return out.reshape(())
+    return _device.to_host(out)[0, 0]  # numpy scalar of the input precision, like the reference
+
+
+def simpleKernelSoap(x, y):
+    """a simpler SOAP Kernel than :func:`kernelSoap`, power is always 1 (distances.py:7-19)."""
+    return _pair(x, y, _lib.KIND_COSCLIP)
+
+
+def simpleSOAPdistance(x, y):
+    """a simpler SOAP distance than :func:`SOAPdistance`, power is always 1 (distances.py:22-35)."""
+    return _pair(x, y, _lib.KIND_SIMPLE)
+
+
+def kernelSoap(x, y, n: int):
+    """The SOAP Kernel with a variable power (distances.py:38-51)."""
+    return _pair(x, y, _lib.KIND_DOT, n)
+
+
+def SOAPdistance(x, y, n: int = 1):
+    """the SOAP distance between two SOAP fingerprints (distances.py:54-68)."""
+    return _pair(x, y, _lib.KIND_KERNEL, n)
+
+
+def SOAPdistanceNormalized(x, y):
+    """the SOAP distance between two normalized SOAP fingerprints (distances.py:71-83)."""
+    return _pair(x, y, _lib.KIND_NORMALIZED)
+
+
+def kernelSOAPdistance(x, y, n: int = 1):
+    """North-star alias of :func:`SOAPdistance` (no reference symbol has this name)."""
+    return SOAPdistance(x, y, n)
+
+
+# ---- dispatch of ``distanceFunction`` / ``distanceCalculator`` callables -----------------------
+_KINDS = {
+    simpleSOAPdistance: (_lib.KIND_SIMPLE, 1),
+    SOAPdistance: (_lib.KIND_KERNEL, 1),
+    kernelSOAPdistance: (_lib.KIND_KERNEL, 1),
+    SOAPdistanceNormalized: (_lib.KIND_NORMALIZED, 1),
+    simpleKernelSoap: (_lib.KIND_COSCLIP, 1),
+}
+
+
+def resolve_distance(fn) -> "tuple[int, int]":
+    """(kind, power) for one of the built-in distances, ``functools.partial(SOAPdistance, n=k)`` included."""
+    if isinstance(fn, functools.partial):
+        base = fn.func
+        if base in (SOAPdistance, kernelSOAPdistance, kernelSoap) and not fn.args:
+            extra = set(fn.keywords) - {"n"}
+            if not extra:
+                n = int(fn.keywords.get("n", 1))
+                return (_lib.KIND_DOT if base is kernelSoap else _lib.KIND_KERNEL), n
+        raise NotImplementedError(f"unsupported partial distance {fn!r}")
+    try:
+        return _KINDS[fn]
+    except (KeyError, TypeError):
+        raise NotImplementedError(
+            "cpctools_b200 runs the built-in SOAP distances on the GPU (simpleSOAPdistance, SOAPdistance, "
+            "functools.partial(SOAPdistance, n=k), SOAPdistanceNormalized); an arbitrary Python callable "
+            f"would need a CPU loop, which this package does not have: {fn!r}"
+        ) from None

@@ -1,0 +1,130 @@
+/*
+ * soap_b200.h -- C ABI of libsoapb200.so: the SOAP post-processing hot path of
+ * GMPavanLab/cpctools (SOAPify) as hand-written sm_100a CUDA kernels.
+ *
+ * The reference is pure Python (no FFI of its own): the functions below are what a
+ * ctypes binding inside SOAPify would call in place of the numpy bodies cited on each
+ * entry (file:line relative to the reference tree).  INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all
+ *     buffers; nothing is allocated or freed behind the caller's back;
+ *   - arrays are C-contiguous (row-major), vectors on the last axis;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call
+ *     is asynchronous on that stream and returns right after the launch;
+ *   - return value: 0 on success, a negative SOAP_E* code otherwise; soap_last_error()
+ *     gives the message for the calling thread.  No C++ exception crosses the boundary;
+ *   - dtype codes: SOAP_F32 / SOAP_F64 select the arithmetic type of the data; integer data
+ *     is only ever gathered (soap_expand takes an element size).
+ */
+#ifndef SOAP_B200_H
+#define SOAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOAP_B200_ABI_VERSION 1
+
+enum { SOAP_F32 = 0, SOAP_F64 = 1 };
+
+/* distance kinds: src/SOAPify/distances.py */
+enum {
+  SOAP_KIND_SIMPLE = 0,     /* simpleSOAPdistance   distances.py:22-35 (scipy cosine, clipped)      */
+  SOAP_KIND_KERNEL = 1,     /* SOAPdistance(n)      distances.py:54-68 (no clip, NaN if k > 1)      */
+  SOAP_KIND_NORMALIZED = 2, /* SOAPdistanceNormalized distances.py:71-83 (sqrt|2-2 x.y|)            */
+  SOAP_KIND_DOT = 3,        /* kernelSoap(n): the kernel value (x.y/|x||y|)^n, distances.py:38-51 */
+  SOAP_KIND_COSCLIP = 4,    /* simpleKernelSoap: 1 - clip(1 - x.y/sqrt(xx yy), 0, 2), distances.py:7-19 */
+  SOAP_KIND_EUCLID = 5,     /* |x - y|_2 : the per-frame norm of timeSOAPsimple, analysis.py:136    */
+  SOAP_KIND_NORMALIZED_FUSED = 6 /* normalizeArray (utils.py:140-153, zero norm -> 1) folded into
+                               SOAPdistanceNormalized: sqrt|2 - 2 x.y/(nx ny)| on RAW vectors   */
+};
+
+enum {
+  SOAP_OK = 0,
+  SOAP_EINVAL = -1,   /* bad argument (message says which)                     */
+  SOAP_ECUDA = -2,    /* CUDA runtime / driver error (message carries the text) */
+  SOAP_EUNSUPPORTED = -3
+};
+
+/* library / device ---------------------------------------------------------------- */
+int soap_abi_version(void);
+const char *soap_last_error(void);
+/* number of kernels launched through this library by the calling process so far
+ * (bench.py reports the delta over its timed region as "gpu_launches") */
+int64_t soap_launch_count(void);
+
+/* profiling hook (bench.py): while enabled, every call brackets its MAIN kernel (the one that moves
+ * the data: expand, time-lag walk, tensor-core pair tiles) with CUDA events recorded on the call's
+ * own stream.  soap_profile_read waits for the recorded events, writes the elapsed milliseconds of
+ * the calls of `kernel_id` (SOAP_PROF_*) since the last enable, oldest first, and returns how
+ * many there were (at most `capacity` are written). */
+enum { SOAP_PROF_EXPAND = 0, SOAP_PROF_TIMELAG = 1, SOAP_PROF_PAIRS = 2 };
+int soap_profile_enable(int on);
+int soap_profile_read(int kernel_id, float *ms_out_host, int capacity);
+
+/* ---- expansion: fillSOAPVectorFromdscribe, utils.py:271-324 --------------------------
+ * out[v][j] = in[v][idx[j]], v < nvec, j < d_full.  Pure gather, bit-exact, any element type
+ * of 4 or 8 bytes (elem_size).  `idx` is the table of utils.py:212-268 (or its composition
+ * with the quippy permutation utils.py:112-137 / engine.py:260), int32, device memory.
+ * in_row_stride = elements between consecutive input rows (>= max(idx)+1; 1198 for raw quippy).
+ */
+int soap_expand(const void *in, void *out, const int32_t *idx, int64_t nvec, int in_row_stride,
+                int d_full, int elem_size, void *stream);
+
+/* ---- expansion fused with normalizeArray (utils.py:271-324 then utils.py:140-153) -----
+ * out[v][j] = in[v][idx[j]] / norm_v, norm_v = sqrt(sum_j in[v][idx[j]]^2), norm_v == 0 -> 1.
+ * idx == NULL means identity (d_full == in_row_stride): plain normalizeArray.
+ * dtype SOAP_F32 / SOAP_F64 (float types only; integer input is promoted by the caller).
+ */
+int soap_expand_normalize(const void *in, void *out, const int32_t *idx, int64_t nvec,
+                          int in_row_stride, int d_full, int dtype, void *stream);
+
+/* ---- time-lagged per-atom distances: timeSOAP, analysis.py:13-69 ------------------------
+ * X[F][A][D] (dtype), optional slot multiplicities mult[D] (same dtype as X, or NULL = all 1):
+ * with mult = bincount of the gather table the distances are those of the EXPANDED vectors
+ * without materialising them (the dot products of utils.py:271's output are weighted dots of
+ * its input).  For each window w_k (k < n_windows <= SOAP_MAX_WINDOWS):
+ *     t_k[f - w_k][a] = dist(X[f][a][:], X[f - w_k][a][:]),  w_k <= f < F
+ * written to t + t_offsets_host[k] (doubles; each block is [F - w_k][A] row-major, always
+ * float64 like analysis.py:53).  All windows are produced by ONE pass over X.
+ * `scratch` must hold soap_timelag_scratch_bytes(...) bytes.
+ */
+#define SOAP_MAX_WINDOWS 4
+size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, int dim, int dtype,
+                                  const int *windows_host, int n_windows);
+int soap_timelag(const void *X, const void *mult, double *t, const int64_t *t_offsets_host,
+                 int64_t n_frames, int64_t n_atoms, int dim, const int *windows_host,
+                 int n_windows, int kind, int power, int dtype, void *scratch, void *stream);
+
+/* ---- numpy.diff(t.T, axis=-1): analysis.py:67,141,203 -----------------------------------
+ * t[rows][A] -> dt[A][rows-1], dt[a][r] = t[r+1][a] - t[r][a].
+ */
+int soap_diff_transposed(const double *t, double *dt, int64_t rows, int64_t n_atoms, void *stream);
+
+/* ---- distance matrix: getDistanceBetween, classify.py:96-117 ---------------------------
+ * out[i][j] = dist(data[i], spectra[j]); data[n_data][D], spectra[n_spectra][D] (dtype);
+ * out has leading dimension ldo (elements) and the type of `dtype` (classify.py:113).
+ * path: SOAP_PAIRS_AUTO picks; SOAP_PAIRS_SIMT = CUDA-core tiles (any size);
+ * SOAP_PAIRS_TENSOR = tensor-core GEMM (fp64: DMMA m8n8k4; fp32: tcgen05 3xTF32).
+ * If argmin_out / min_out are non-NULL the row-wise argmin (int32) / min (double) over j is
+ * produced as well (applyClassification, classify.py:274-275) and `out` may be NULL.
+ */
+enum { SOAP_PAIRS_AUTO = 0, SOAP_PAIRS_SIMT = 1, SOAP_PAIRS_TENSOR = 2 };
+size_t soap_pairs_scratch_bytes(int64_t n_data, int64_t n_spectra, int dim, int dtype, int path);
+int soap_pairs(const void *data, const void *spectra, void *out, int64_t n_data, int64_t n_spectra,
+               int dim, int64_t ldo, int kind, int power, int dtype, int path, int32_t *argmin_out,
+               double *min_out, void *scratch, void *stream);
+
+/* ---- synthetic data for the benchmarks (counter-based hash RNG, reproducible) ------------
+ * fills n elements of `dtype` with uniform [0,1) values derived from (seed, element index).
+ */
+int soap_fill_uniform(void *out, int64_t n, uint64_t seed, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOAP_B200_H */

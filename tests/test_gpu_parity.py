@@ -1,0 +1,382 @@
+"""Parity of the CUDA path (through the C ABI of libsoapb200.so) with the CPU oracle and with the
+golden vectors generated from the unmodified reference.  All tests need a B200: ``-m gpu``.
+
+Tolerances (written here once, see tests/parity.py): integer / gather work bit-exact;
+normalisation 1e-12 relative (fp64), 1e-6 (fp32); distances by ``assert_distance_parity``
+(d^2 to 1e-12 absolute, d to 1e-12 relative where d >= 0.1; 1e-6 for the fp32 path).
+"""
+import functools
+import warnings
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from oracle import soap_oracle as O
+from oracle.fake_dataset import FakeSOAPDataset, dscribe_attrs, synthetic_soap
+from oracle.gen_golden import _slices_from_attrs
+from parity import assert_distance_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import cpctools_b200
+
+    cpctools_b200._lib.load()  # fail loudly if the extension was not built
+    return cpctools_b200
+
+
+def _kinds(S):
+    return {
+        "simple": (S.simpleSOAPdistance, O.KIND_SIMPLE, 1),
+        "kernel1": (S.SOAPdistance, O.KIND_KERNEL, 1),
+        "kernel2": (functools.partial(S.SOAPdistance, n=2), O.KIND_KERNEL, 2),
+        "normalized": (S.SOAPdistanceNormalized, O.KIND_NORMALIZED, 1),
+    }
+
+
+# ------------------------------------------------------------------ expansion: bit-exact
+def test_fill_matches_golden_bit_exact(S, golden):
+    g = golden("fill_norm")
+    out = S.fillSOAPVectorFromdscribe(g["fill1_in_f64"], 8, 8)
+    assert out.dtype == np.float64 and out.shape == (6, 4, 576)
+    assert_array_equal(out, g["fill1_out_f64"])
+    out32 = S.fillSOAPVectorFromdscribe(g["fill1_in_f64"].astype(np.float32), 8, 8)
+    assert out32.dtype == np.float32
+    assert_array_equal(out32, g["fill1_out_f32"])
+    outi = S.fillSOAPVectorFromdscribe(g["fill1_in_i64"], 8, 8)
+    assert outi.dtype == g["fill1_out_i64"].dtype
+    assert_array_equal(outi, g["fill1_out_i64"])
+    assert_array_equal(S.fillSOAPVectorFromdscribe(g["fill1_in_1d"], 8, 8), g["fill1_out_1d"])
+    attrs, _ = dscribe_attrs(8, 8, ["H", "O"])
+    out2 = S.fillSOAPVectorFromdscribe(g["fill2_in_f64"], 8, 8, ["O", "H"], _slices_from_attrs(attrs))
+    assert_array_equal(out2, g["fill2_out_f64"])
+    # quippy raw rows (trailing column, quippy slot order) through ONE composed gather
+    attrs3, _ = dscribe_attrs(6, 6, ["H", "C", "O"])
+    out3 = S.fillSOAPVectorFromQuip(g["quip3_in_raw"], 6, 6, ["O", "H", "C"], _slices_from_attrs(attrs3))
+    assert_array_equal(out3, g["quip3_out_f64"])
+    out3b = S.fillSOAPVectorFromQuip(g["quip3_in_raw"], 6, 6, ["H", "C", "O"])  # default container slices
+    assert_array_equal(out3b, g["quip3_out_f64"])
+
+
+@pytest.mark.parametrize("nmax", [1, 3, 4, 8])
+@pytest.mark.parametrize("lmax", [0, 3, 4, 8])
+@pytest.mark.parametrize("species", [None, ["O", "H"], ["H", "C", "O"]])
+def test_fill_matches_oracle_all_layouts(S, nmax, lmax, species):
+    """reference tests/test_SOAPify.py:135-240 (single, array, multi-species; integer equality)
+    extended to odd row lengths (unaligned rows take the non-TMA path)."""
+    rng = np.random.default_rng(100 * nmax + lmax)
+    if species is None:
+        kw, dc = {}, (lmax + 1) * nmax * (nmax + 1) // 2
+    else:
+        attrs, dc = dscribe_attrs(lmax, nmax, O.orderByZ(species))
+        kw = dict(atomTypes=species, atomicSlices=_slices_from_attrs(attrs))
+    for shape, dtype in (((dc,), np.int64), ((7, dc), np.float64), ((5, 11, dc), np.float32), ((3, 2, dc), np.int32)):
+        a = rng.integers(0, 10, size=shape).astype(dtype)
+        want = O.fillSOAPVectorFromdscribe(a, lmax, nmax, **kw)
+        got = S.fillSOAPVectorFromdscribe(a, lmax, nmax, **kw)
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert_array_equal(got, want)
+    with pytest.raises(Exception):
+        S.fillSOAPVectorFromdscribe(rng.integers(0, 10, size=(5, dc + 1)), lmax, nmax, **kw)
+    with pytest.raises(Exception):
+        S.fillSOAPVectorFromdscribe(rng.integers(0, 10, size=(3, 4, 5, dc)), lmax, nmax, **kw)
+
+
+def test_fill_large_tiles_and_ragged_tail(S):
+    """many tiles per CTA, a ragged last tile, and an empty input."""
+    rng = np.random.default_rng(5)
+    attrs, dc = dscribe_attrs(8, 8, ["H", "O"])
+    sl = _slices_from_attrs(attrs)
+    a = rng.random((97, 131, dc))
+    assert_array_equal(S.fillSOAPVectorFromdscribe(a, 8, 8, ["H", "O"], sl), O.fillSOAPVectorFromdscribe(a, 8, 8, ["H", "O"], sl))
+    empty = np.zeros((0, dc))
+    assert S.fillSOAPVectorFromdscribe(empty, 8, 8, ["H", "O"], sl).shape == (0, 1728)
+
+
+def test_fill_device_tensor_stays_on_device(S):
+    import torch
+
+    x = torch.rand(4, 3, 324, dtype=torch.float64, device="cuda")
+    y = S.fillSOAPVectorFromdscribe(x, 8, 8)
+    assert isinstance(y, torch.Tensor) and y.is_cuda and y.shape == (4, 3, 576)
+    assert_array_equal(y.cpu().numpy(), O.fillSOAPVectorFromdscribe(x.cpu().numpy(), 8, 8))
+
+
+# ------------------------------------------------------------------ normalisation
+def test_normalize_known_answers(S):
+    """reference tests/test_SOAPify.py:19-41 (exact)."""
+    assert_array_equal(S.normalizeArray(np.array([2.0, 0.0])), [1.0, 0.0])
+    assert_array_equal(S.normalizeArray(np.array([[2.0, 0.0, 0.0], [0.0, 0.0, 3.0]])), [[1.0, 0, 0], [0, 0, 1.0]])
+    a = np.array([[[2.0, 0.0, 0.0], [0.0, 0.0, 3.0]], [[0.0, 2.0, 0.0], [0.0, 3.0, 0.0]]])
+    assert_array_equal(S.normalizeArray(a), [[[1.0, 0, 0], [0, 0, 1.0]], [[0, 1.0, 0], [0, 1.0, 0]]])
+
+
+def test_normalize_matches_golden(S, golden):
+    g = golden("fill_norm")
+    assert_allclose(S.normalizeArray(g["fill1_out_f64"]), g["norm1_out_f64"], rtol=1e-12, atol=0)
+    n32 = S.normalizeArray(g["fill1_out_f32"])
+    assert n32.dtype == np.float32
+    assert_allclose(n32, g["norm1_out_f32"], rtol=1e-6, atol=0)
+    ni = S.normalizeArray(g["fill1_out_i64"])  # integer input is promoted to float64
+    assert ni.dtype == np.float64
+    assert_allclose(ni, g["norm1_out_i64"], rtol=1e-12, atol=0)
+    n2 = S.normalizeArray(g["fill2_out_f64"])
+    assert_allclose(n2, g["norm2_out_f64"], rtol=1e-12, atol=0)
+    assert not n2[1, 2].any()  # the all-zero vector stays zero
+    # fused expand+normalise == the two reference steps
+    attrs, _ = dscribe_attrs(8, 8, ["H", "O"])
+    fused = S.fillAndNormalize(g["fill2_in_f64"], 8, 8, ["O", "H"], _slices_from_attrs(attrs))
+    assert_allclose(fused, g["norm2_out_f64"], rtol=1e-12, atol=0)
+    fq = S.fillAndNormalize(g["quip3_in_raw"], 6, 6, ["H", "C", "O"], quippy=True)
+    assert_allclose(fq, g["quip3_norm_f64"], rtol=1e-12, atol=0)
+
+
+# ------------------------------------------------------------------ scalar distances
+def test_math_matches_golden(S, golden):
+    """reference tests/test_SOAPifySOAP.py:339-376 (decimal 8 there; 1e-12 here)."""
+    g = golden("math")
+    for c in range(5):
+        x, y = g[f"x{c}"], g[f"y{c}"]
+        xn, yn = x / np.linalg.norm(x), y / np.linalg.norm(y)
+        vals = [S.simpleKernelSoap(x, y), S.simpleSOAPdistance(x, y), S.SOAPdistanceNormalized(xn, yn)]
+        vals += [S.kernelSoap(x, y, n) for n in range(1, 10)]
+        vals += [S.SOAPdistance(x, y, n) for n in range(1, 10)]
+        want = g[f"vals{c}"]
+        assert_allclose(np.array(vals)[[0] + list(range(3, 12))], want[[0] + list(range(3, 12))], rtol=0, atol=1e-12)
+        assert_distance_parity(np.array(vals)[[1, 2] + list(range(12, 21))], want[[1, 2] + list(range(12, 21))], "f64")
+        xf, yf = x.astype(np.float32), y.astype(np.float32)
+        vf = [S.simpleSOAPdistance(xf, yf), S.SOAPdistance(xf, yf, 1), S.SOAPdistance(xf, yf, 2),
+              S.SOAPdistanceNormalized(xf / np.linalg.norm(xf), yf / np.linalg.norm(yf))]
+        assert all(np.asarray(v).dtype == np.float32 for v in vf)
+        assert_distance_parity(np.array(vf), g[f"vals_f32_{c}"], "f32")
+
+
+def test_self_and_zero_distances(S, golden):
+    g = golden("math")
+    X = g["self_in"]
+    z = np.zeros(576)
+    assert np.isnan(S.simpleSOAPdistance(z, X[0])) and np.isnan(S.SOAPdistance(z, X[0]))
+    assert S.SOAPdistanceNormalized(z, X[0] / np.linalg.norm(X[0])) == np.sqrt(2.0)
+    d = S.getDistanceBetween(X, X, S.simpleSOAPdistance)
+    assert (np.diag(d) == 0.0).all()  # the scipy clip makes self distances exactly 0
+    assert_distance_parity(np.diag(S.getDistanceBetween(X, X, S.SOAPdistance)), g["self_kernel1"], "f64")
+    Xn = O.normalizeArray(X)
+    assert_distance_parity(np.diag(S.getDistanceBetween(Xn, Xn, S.SOAPdistanceNormalized)), g["self_normalized"], "f64")
+
+
+def test_unknown_callable_is_refused(S):
+    X = np.random.default_rng(0).random((4, 3, 8))
+    with pytest.raises(NotImplementedError):
+        S.timeSOAP(X, distanceFunction=lambda a, b: 0.0)
+    with pytest.raises(NotImplementedError):
+        S.getDistanceBetween(X[0], X[1], lambda a, b: 0.0)
+
+
+# ------------------------------------------------------------------ timeSOAP family
+@pytest.mark.parametrize("dist", ["U", "W"])
+def test_timesoap_matches_golden(S, golden, dist):
+    g = golden("timesoap")
+    raw = g[f"{dist}_raw"]
+    X = O.fillSOAPVectorFromdscribe(raw, 8, 8)
+    Xn = O.normalizeArray(X)
+    K = _kinds(S)
+    for w in (1, 2, 5):
+        t, dt = S.timeSOAP(Xn, window=w)
+        assert t.dtype == np.float64 and t.shape == (14 - w, 5) and dt.shape == (5, 13 - w)
+        assert_distance_parity(t, g[f"{dist}_simple_w{w}_t"], "f64", what=f"simple w{w}")
+        assert_array_equal(dt, np.diff(t.T, axis=-1))  # the diff kernel is exact on its input
+        assert_distance_parity(S.timeSOAP(X, window=w, returnDiff=False), g[f"{dist}_simple_raw_w{w}_t"], "f64")
+        for name in ("kernel1", "kernel2"):
+            got = S.timeSOAP(X, window=w, returnDiff=False, distanceFunction=K[name][0])
+            assert_distance_parity(got, g[f"{dist}_{name}_w{w}_t"], "f64", what=f"{name} w{w}")
+        got = S.timeSOAP(Xn, window=w, returnDiff=False, distanceFunction=S.SOAPdistanceNormalized)
+        assert_distance_parity(got, g[f"{dist}_normalized_w{w}_t"], "f64", what=f"normalized w{w}")
+        ts, dts = S.timeSOAPsimple(Xn, window=w)
+        assert_allclose(ts, g[f"{dist}_tsimple_w{w}_t"], rtol=1e-12, atol=1e-15)
+        assert_allclose(dts, g[f"{dist}_tsimple_w{w}_dt"], rtol=0, atol=1e-13)
+        # straight from the compressed data (expansion + normalisation folded in)
+        for name, key in (("simple", "simple"), ("kernel2", "kernel2"), ("normalized", "normalized")):
+            (got,) = S.timeSOAPfromCompressed(raw, 8, 8, windows=(w,), returnDiff=False, distanceFunction=K[name][0])
+            assert_distance_parity(got, g[f"{dist}_{key}_w{w}_t"], "f64", what=f"compressed {name} w{w}")
+    t32 = S.timeSOAP(Xn.astype(np.float32), window=1, returnDiff=False)
+    assert t32.dtype == np.float64  # analysis.py:53
+    assert_distance_parity(t32, g[f"{dist}_simple_w1_t"], "f32")
+
+
+def test_timesoap_errors(S):
+    """reference tests/test_analysis.py:41,46 pin these substrings."""
+    X = np.zeros((10, 2, 4))
+    with pytest.raises(ValueError, match="the window must be bigger than the stride"):
+        S.timeSOAP(X, window=2, stride=3)
+    with pytest.raises(ValueError, match="stride and window must be smaller than simulation lenght"):
+        S.timeSOAP(X, window=10)
+    with pytest.raises(ValueError, match="stride and window must be smaller"):
+        S.timeSOAPsimple(X, window=11)
+
+
+@pytest.mark.parametrize(
+    "F,A,species,dtype,windows",
+    [
+        (70, 37, 1, np.float64, (1, 5, 10, 50)),     # config-1 vector, the benchmark's delay sweep
+        (131, 9, 2, np.float64, (1, 5, 10, 50)),     # config-2/3 vector: rows are split into pieces
+        (131, 9, 2, np.float32, (1, 5, 10, 50)),
+        (40, 6, 3, np.float64, (1, 7)),              # config-5 vector (Dc 1197: unaligned rows)
+        (33, 3, 1, np.float64, (32,)),               # a window as long as one ring block
+        (200, 2, 1, np.float64, (150,)),             # a window of many blocks
+    ],
+)
+def test_timesoap_sweep_from_compressed_vs_oracle(S, F, A, species, dtype, windows):
+    sp = {1: None, 2: ["H", "O"], 3: ["H", "C", "O"]}[species]
+    l = n = 6 if species == 3 else 8
+    if sp is None:
+        kw, dc = {}, (l + 1) * n * (n + 1) // 2
+    else:
+        attrs, dc = dscribe_attrs(l, n, sp)
+        kw = dict(atomTypes=sp, atomicSlices=_slices_from_attrs(attrs))
+    raw = synthetic_soap((F, A, dc), seed=F + A, kind="W", dtype=dtype)
+    X = O.normalizeArray(O.fillSOAPVectorFromdscribe(raw.astype(np.float64), l, n, **kw))
+    path = "f64" if dtype == np.float64 else "f32"
+    got = S.timeSOAPfromCompressed(raw, l, n, windows=windows, **kw)
+    mat = S.timeSOAPsweep(X.astype(dtype), windows=windows)
+    for w, (t, dt), (tm, dtm) in zip(windows, got, mat):
+        want, wdt = O.timeSOAP_batched(X, window=w, kind=O.KIND_SIMPLE)
+        assert t.shape == want.shape and dt.shape == wdt.shape
+        assert_distance_parity(t, want, path, what=f"compressed w{w}")
+        assert_distance_parity(tm, want, path, what=f"materialised w{w}")
+        assert_array_equal(dt, np.diff(t.T, axis=-1))
+        if dtype == np.float64:
+            eu = S.timeSOAPsimple(X, window=w, returnDiff=False) if w == 1 else None
+            if eu is not None:
+                assert_allclose(eu, np.linalg.norm(X[1:] - X[:-1], axis=-1), rtol=1e-12, atol=1e-15)
+
+
+def test_streaming_shortcut_matches_golden(S, golden):
+    g = golden("timesoap")
+    attrs1 = {"l_max": 8, "n_max": 8, "species": ["H"], "species_location_H-H": [0, 324]}
+    t, dt = S.getTimeSOAPSimple(FakeSOAPDataset(g["stream_raw"], 10, attrs1))
+    assert t.shape == (46, 5) and dt.shape == (5, 45)
+    assert_allclose(t, g["stream_t"], rtol=1e-12, atol=1e-15)
+    assert_allclose(dt, g["stream_dt"], rtol=0, atol=1e-13)
+    attrs2, _ = dscribe_attrs(4, 4, ["H", "O"])
+    t2, dt2 = S.getTimeSOAPSimple(FakeSOAPDataset(g["stream2_raw"], 6, attrs2))
+    assert_allclose(t2, g["stream2_t"], rtol=1e-12, atol=1e-15)
+    # window > 1: the reference raises; here the chunks are stitched with a `window`-frame halo
+    raw = g["stream_raw"]
+    t5, _ = S.getTimeSOAPSimple(FakeSOAPDataset(raw, 10, attrs1), window=5)
+    Xn = O.normalizeArray(O.fillSOAPVectorFromdscribe(raw, 8, 8))
+    assert_allclose(t5, np.linalg.norm(Xn[5:] - Xn[:-5], axis=-1), rtol=1e-12, atol=1e-15)
+    # chunk shorter than the window
+    t7, _ = S.getTimeSOAPSimple(FakeSOAPDataset(raw, 3, attrs1), window=7)
+    assert_allclose(t7, np.linalg.norm(Xn[7:] - Xn[:-7], axis=-1), rtol=1e-12, atol=1e-15)
+
+
+# ------------------------------------------------------------------ distance matrix / classification
+def test_distance_matrix_matches_golden(S, golden):
+    g = golden("classify")
+    data, spectra = g["data"], g["spectra"]
+    K = _kinds(S)
+    assert_distance_parity(S.getDistanceBetween(data, spectra, S.SOAPdistanceNormalized), g["dm_normalized"], "f64")
+    assert_distance_parity(S.getDistanceBetween(data, spectra, S.simpleSOAPdistance), g["dm_simple"], "f64")
+    assert_distance_parity(S.getDistanceBetween(data, spectra, K["kernel2"][0]), g["dm_kernel2"], "f64")
+    assert_distance_parity(S.getDistanceBetween(data, data, S.SOAPdistance), g["dm_self_kernel1"], "f64")
+    assert_distance_parity(S.getDistanceBetween(data, data, S.SOAPdistanceNormalized), g["dm_self_normalized"], "f64")
+    d32 = S.getDistanceBetween(data.astype(np.float32), spectra.astype(np.float32), S.SOAPdistanceNormalized)
+    assert d32.dtype == np.float32 and d32.shape == (37, 9)
+    assert_distance_parity(d32, g["dm_normalized_f32"], "f32")
+
+
+@pytest.mark.parametrize("M,K,D", [(1, 1, 3), (65, 130, 50), (300, 7, 576), (129, 257, 1728)])
+def test_distance_matrix_shapes_vs_oracle(S, M, K, D):
+    rng = np.random.default_rng(M + K + D)
+    a, b = rng.random((M, D)), rng.random((K, D))
+    for name, (fn, kind, power) in _kinds(S).items():
+        src_a, src_b = (O.normalizeArray(a), O.normalizeArray(b)) if name == "normalized" else (a, b)
+        want = O.getDistanceBetween_batched(src_a, src_b, kind, power)
+        assert_distance_parity(S.getDistanceBetween(src_a, src_b, fn), want, "f64", what=name)
+
+
+def test_classification_matches_golden(S, golden):
+    g = golden("classify")
+    attrs = {"l_max": 8, "n_max": 8, "species": ["Au"], "species_location_Au-Au": [0, 324]}
+    ds = FakeSOAPDataset(g["cls_raw"], 1000, attrs)
+    refs = S.SOAPReferences(["a", "b", "c", "d"], g["cls_ref_spectra"], 8, 8)
+    d = S.getDistancesFromRefNormalized(ds, refs)
+    assert d.shape == g["cls_dist"].shape and d.dtype == np.float64
+    assert_distance_parity(d, g["cls_dist"], "f64")
+    cl = S.applyClassification(ds, refs, S.SOAPdistanceNormalized, doNormalize=True)
+    assert cl.legend == ["a", "b", "c", "d"]
+    assert_distance_parity(cl.distances, g["cls_min"], "f64")
+    # argmin may only differ where two references are equidistant to rounding
+    differ = cl.references != g["cls_arg"]
+    if differ.any():
+        srt = np.sort(g["cls_dist"], axis=-1)
+        assert (np.abs(srt[..., 1] ** 2 - srt[..., 0] ** 2)[differ] <= 1e-12).all()
+    assert_distance_parity(S.getDistancesFromRef(ds, refs, S.simpleSOAPdistance, doNormalize=False), g["cls_dist_simple"], "f64")
+    # references built through the GPU expand/normalise match the reference-built ones
+    built = S.createReferencesFromTrajectory(ds, {"a": (0, 0), "b": (100, 3), "c": (129, 1), "d": (17, 2)}, 8, 8)
+    assert_allclose(built.spectra, g["cls_ref_spectra"], rtol=1e-12, atol=0)
+    part = S.getDistancesFromInterval(ds, refs, S.SOAPdistanceNormalized, True, slice(20, 57))
+    assert_distance_parity(part, g["cls_dist"][20:57], "f64")
+
+
+def test_argmin_numpy_rules(S):
+    """ties -> first index; NaN -> first NaN (numpy.argmin / amin, classify.py:274-275)."""
+    import torch
+    from cpctools_b200.classify import pairs_device
+    from cpctools_b200 import _lib
+
+    rng = np.random.default_rng(3)
+    data = rng.random((70, 40))
+    refs = rng.random((9, 40))
+    refs[5] = refs[2]  # exact tie
+    refs[7] = 0.0      # zero reference -> NaN under the clipped cosine
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = O.getDistanceBetween_batched(data, refs, O.KIND_SIMPLE, 1)
+    amin, arg = pairs_device(torch.from_numpy(data).cuda(), torch.from_numpy(refs).cuda(), _lib.KIND_SIMPLE, 1, want_argmin=True)
+    assert (arg.cpu().numpy() == np.argmin(want, axis=-1)).all() and (arg.cpu().numpy() == 7).all()
+    assert np.isnan(amin.cpu().numpy()).all()
+    amin, arg = pairs_device(torch.from_numpy(data).cuda(), torch.from_numpy(refs[:7]).cuda(), _lib.KIND_SIMPLE, 1, want_argmin=True)
+    full = S.getDistanceBetween(data, refs[:7], S.simpleSOAPdistance)
+    assert_array_equal(arg.cpu().numpy(), np.argmin(full, axis=-1))
+    assert_array_equal(amin.cpu().numpy(), np.amin(full, axis=-1))
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_properties_at_benchmark_row_sizes(S):
+    """Config-2/3 vectors (2 species, Dc 1224 -> Df 1728) on device-generated data too large for the
+    Python oracle: (i) expansion == gather by the table, checked by multiplicity-weighted sums;
+    (ii) normalised rows have unit norm; (iii) the distances are invariant under per-vector
+    rescaling and under the expansion itself (compressed path == materialised path);
+    (iv) a trajectory that repeats with period p has t_p == 0 exactly under the clipped kernel."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.analysis import timelag_device
+
+    attrs, dc = dscribe_attrs(8, 8, ["H", "O"])
+    sl = _slices_from_attrs(attrs)
+    F, A = 96, 600
+    raw = torch.empty((F, A, dc), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().soap_fill_uniform(raw.data_ptr(), raw.numel(), 12345, _lib.F64, None))
+    torch.cuda.synchronize()
+    plan = S.getExpansionPlan(8, 8, ["H", "O"], sl)
+    full = S.fillSOAPVectorFromdscribe(raw, 8, 8, ["H", "O"], sl)
+    mult = plan.multiplicity_device(torch.float64)
+    assert torch.allclose(full.sum(-1), (raw * mult).sum(-1), rtol=1e-13, atol=0)
+    assert torch.equal(full, raw[..., torch.from_numpy(plan.index).cuda()])
+    nrm = S.fillAndNormalize(raw, 8, 8, ["H", "O"], sl)
+    assert torch.allclose(nrm.norm(dim=-1), torch.ones(F, A, dtype=torch.float64, device="cuda"), rtol=1e-14, atol=0)
+    windows = (1, 5, 10, 50)
+    t_mat = timelag_device(nrm, windows, _lib.KIND_SIMPLE)
+    t_cmp = timelag_device(raw, windows, _lib.KIND_SIMPLE, mult=mult)
+    scale = torch.rand(F, A, 1, dtype=torch.float64, device="cuda") + 0.5
+    t_scl = timelag_device(raw * scale, windows, _lib.KIND_SIMPLE, mult=mult)
+    for a, b, c in zip(t_mat, t_cmp, t_scl):
+        assert_distance_parity(b.cpu().numpy(), a.cpu().numpy(), "f64")
+        assert_distance_parity(c.cpu().numpy(), a.cpu().numpy(), "f64")
+    periodic = raw[:5].repeat(12, 1, 1)
+    (t5,) = timelag_device(periodic, (5,), _lib.KIND_SIMPLE, mult=mult)
+    assert (t5 == 0).all()
