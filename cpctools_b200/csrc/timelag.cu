@@ -27,8 +27,8 @@
 
 namespace soapb {
 
-constexpr int kTlThreads = 256;
-constexpr int kTlWarps = kTlThreads / 32;
+constexpr int kTlWarps = 8;                      // consumer warps
+constexpr int kTlThreads = (kTlWarps + 2) * 32;  // + producer warp + reducer warp
 constexpr int kBlk = 32;  // frames per block == lanes per warp
 
 struct TimelagPlan {
@@ -37,7 +37,7 @@ struct TimelagPlan {
 };
 
 static size_t tl_smem_bytes(int R, int stride, int upp, int Q) {
-  return (size_t)R * stride + (size_t)upp * 16 + (size_t)kTlWarps * Q * 32 * 8 + (size_t)(R / kBlk) * 8 + 64;
+  return (size_t)R * stride + (size_t)upp * 16 + (size_t)2 * kTlWarps * Q * 32 * 8 + (size_t)(2 * (R / kBlk) + 4) * 8 + 64;
 }
 
 static int env_int(const char *name, int dflt) {
@@ -59,7 +59,8 @@ static bool make_plan(int D, int elem_size, const int *windows, int nw, TimelagP
     const int real_split = (pl.n_units + upp - 1) / upp;  // no empty pieces
     const int stride = 16 * (upp | 1);
     for (int ahead = force_ahead > 0 ? force_ahead : 3; ahead >= 1; --ahead) {
-      const int R = ((pl.max_lag + kBlk * (ahead + 1) + kBlk - 1) / kBlk) * kBlk;
+      // ring = blocks still needed as lag partners + the block being consumed + `ahead` in flight
+      const int R = kBlk * ((pl.max_lag + kBlk - 1) / kBlk + 1 + ahead);
       const size_t smem = tl_smem_bytes(R, stride, upp, pl.Q);
       if (smem <= budget) {
         pl.split = real_split;
@@ -76,93 +77,152 @@ static bool make_plan(int D, int elem_size, const int *windows, int nw, TimelagP
   return false;
 }
 
-template <typename T>
-struct Vec16;
-template <>
-struct Vec16<double> { using type = double2; };
-template <>
-struct Vec16<float> { using type = float4; };
+// ---- shared-memory access by 32-bit address (keeps the hot loop free of 64-bit pointer math) ----
+__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void cp_async_elem(uint32_t dst, const void *src, int bytes) {
+  if (bytes == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-// one 16-byte unit of frame x against NW lagged frames, accumulated in double
-template <int NW, bool EUCLID>
-__device__ __forceinline__ void accum_unit(const double2 m, const double2 x, const double2 (&y)[NW],
-                                           double (&acc)[NW + 1]) {
-  const double xm0 = x.x * m.x, xm1 = x.y * m.y;
-  acc[0] = fma(xm0, x.x, acc[0]);
-  acc[0] = fma(xm1, x.y, acc[0]);
+// U units (16 bytes each) of the lane's frame against the NW lagged frames.  All loads are issued
+// before the first use so that one warp keeps U*(NW+2) shared-memory requests in flight.
+// fp64: exact products accumulated by DFMA, separate chains for the two halves of a unit.
+template <int NW, int U, bool EUCLID>
+__device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
+                                                uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
+  double2 m[U], x[U], y[NW][U];
 #pragma unroll
-  for (int k = 0; k < NW; ++k) {
-    if (EUCLID) {
-      const double d0 = x.x - y[k].x, d1 = x.y - y[k].y;
-      acc[k + 1] = fma(m.x * d0, d0, acc[k + 1]);
-      acc[k + 1] = fma(m.y * d1, d1, acc[k + 1]);
-    } else {
-      acc[k + 1] = fma(xm0, y[k].x, acc[k + 1]);
-      acc[k + 1] = fma(xm1, y[k].y, acc[k + 1]);
+  for (int j = 0; j < U; ++j) {
+    m[j] = lds_d2(m_addr + off + j * ustep);
+    x[j] = lds_d2(x_addr + off + j * ustep);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) y[k][j] = lds_d2(y_addr[k] + off + j * ustep);
+  }
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const double xm0 = x[j].x * m[j].x, xm1 = x[j].y * m[j].y;
+    acc[0] = fma(xm0, x[j].x, acc[0]);
+    acc[1] = fma(xm1, x[j].y, acc[1]);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+      if (EUCLID) {
+        const double d0 = x[j].x - y[k][j].x, d1 = x[j].y - y[k][j].y;
+        acc[2 * k + 2] = fma(m[j].x * d0, d0, acc[2 * k + 2]);
+        acc[2 * k + 3] = fma(m[j].y * d1, d1, acc[2 * k + 3]);
+      } else {
+        acc[2 * k + 2] = fma(xm0, y[k][j].x, acc[2 * k + 2]);
+        acc[2 * k + 3] = fma(xm1, y[k][j].y, acc[2 * k + 3]);
+      }
     }
   }
 }
 
-// fp32 data: products and an 8-term chain in fp32, chain sums promoted to double (keeps the
-// conversion count at 1/8 per product while bounding the fp32 rounding to one short chain)
-template <int NW, bool EUCLID>
-__device__ __forceinline__ void accum_unit2(const float4 ma, const float4 xa, const float4 (&ya)[NW],
-                                            const float4 mb, const float4 xb, const float4 (&yb)[NW],
-                                            double (&acc)[NW + 1]) {
-  const float a0 = xa.x * ma.x, a1 = xa.y * ma.y, a2 = xa.z * ma.z, a3 = xa.w * ma.w;
-  const float b0 = xb.x * mb.x, b1 = xb.y * mb.y, b2 = xb.z * mb.z, b3 = xb.w * mb.w;
-  float c = a0 * xa.x;
-  c = fmaf(a1, xa.y, c); c = fmaf(a2, xa.z, c); c = fmaf(a3, xa.w, c);
-  c = fmaf(b0, xb.x, c); c = fmaf(b1, xb.y, c); c = fmaf(b2, xb.z, c); c = fmaf(b3, xb.w, c);
-  acc[0] += (double)c;
+// fp32 data: products and a chain of 4*U terms in fp32, chain sums promoted to double (one
+// conversion per 4*U products; the fp32 rounding is bounded to one short chain).
+template <int NW, int U, bool EUCLID>
+__device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
+                                                uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
+  float4 m[U], x[U], y[NW][U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    m[j] = lds_f4(m_addr + off + j * ustep);
+    x[j] = lds_f4(x_addr + off + j * ustep);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) y[k][j] = lds_f4(y_addr[k] + off + j * ustep);
+  }
+  float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    c0 = fmaf(x[j].x * m[j].x, x[j].x, c0);
+    c1 = fmaf(x[j].y * m[j].y, x[j].y, c1);
+    c0 = fmaf(x[j].z * m[j].z, x[j].z, c0);
+    c1 = fmaf(x[j].w * m[j].w, x[j].w, c1);
+  }
+  acc[0] += (double)c0;
+  acc[1] += (double)c1;
 #pragma unroll
   for (int k = 0; k < NW; ++k) {
-    float s;
-    if (EUCLID) {
-      float d;
-      d = xa.x - ya[k].x; s = ma.x * d * d;
-      d = xa.y - ya[k].y; s = fmaf(ma.y * d, d, s);
-      d = xa.z - ya[k].z; s = fmaf(ma.z * d, d, s);
-      d = xa.w - ya[k].w; s = fmaf(ma.w * d, d, s);
-      d = xb.x - yb[k].x; s = fmaf(mb.x * d, d, s);
-      d = xb.y - yb[k].y; s = fmaf(mb.y * d, d, s);
-      d = xb.z - yb[k].z; s = fmaf(mb.z * d, d, s);
-      d = xb.w - yb[k].w; s = fmaf(mb.w * d, d, s);
-    } else {
-      s = a0 * ya[k].x;
-      s = fmaf(a1, ya[k].y, s); s = fmaf(a2, ya[k].z, s); s = fmaf(a3, ya[k].w, s);
-      s = fmaf(b0, yb[k].x, s); s = fmaf(b1, yb[k].y, s); s = fmaf(b2, yb[k].z, s); s = fmaf(b3, yb[k].w, s);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (EUCLID) {
+        const float d0 = x[j].x - y[k][j].x, d1 = x[j].y - y[k][j].y, d2 = x[j].z - y[k][j].z, d3 = x[j].w - y[k][j].w;
+        s0 = fmaf(m[j].x * d0, d0, s0);
+        s1 = fmaf(m[j].y * d1, d1, s1);
+        s0 = fmaf(m[j].z * d2, d2, s0);
+        s1 = fmaf(m[j].w * d3, d3, s1);
+      } else {
+        s0 = fmaf(x[j].x * m[j].x, y[k][j].x, s0);
+        s1 = fmaf(x[j].y * m[j].y, y[k][j].y, s1);
+        s0 = fmaf(x[j].z * m[j].z, y[k][j].z, s0);
+        s1 = fmaf(x[j].w * m[j].w, y[k][j].w, s1);
+      }
     }
-    acc[k + 1] += (double)s;
+    acc[2 * k + 2] += (double)s0;
+    acc[2 * k + 3] += (double)s1;
   }
 }
 
+template <typename T, int NW, int U, bool EUCLID>
+__device__ __forceinline__ void accum_units(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
+                                            uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
+  if constexpr (sizeof(T) == 8)
+    accum_units_f64<NW, U, EUCLID>(m_addr, x_addr, y_addr, off, ustep, acc);
+  else
+    accum_units_f32<NW, U, EUCLID>(m_addr, x_addr, y_addr, off, ustep, acc);
+}
+
+// Warp roles: warps 0..7 consume (lane = frame), warp 8 produces (TMA / cp.async), warp 9 reduces
+// the 8 consumers' partial sums of a block and writes them to scratch.  All hand-offs are
+// mbarriers; there is no __syncthreads after the prologue, so no warp ever convoys behind another.
+//   full[s]      producer -> consumers   block in ring slot-group s has landed
+//   empty[s]     consumers -> producer   block s consumed as "current" frames (8 arrivals)
+//   red_full[i]  consumers -> reducer    partial sums of a block are in red[i] (8 arrivals)
+//   red_empty[i] reducer -> consumers    red[i] may be overwritten
 template <typename T, int NW, bool EUCLID>
 __global__ void __launch_bounds__(kTlThreads, 1)
     timelag_kernel(const T *__restrict__ X, const T *__restrict__ mult, double *__restrict__ scratch,
-                   long long F, long long A, int D, int split, int upp, int stride, int R, int ahead,
+                   long long F, long long A, int D, int split, int upp, int stride, int R, int lag_blocks,
                    int4 win4, int bulk_ok) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int UE = 16 / (int)sizeof(T);
   constexpr int Q = NW + 1;
-  using V = typename Vec16<T>::type;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int win[4] = {win4.x, win4.y, win4.z, win4.w};
+  const int nslots = R / kBlk;
 
   unsigned char *ring = smem_raw;
   unsigned char *msm = ring + (size_t)R * stride;
-  double *red = reinterpret_cast<double *>(msm + (size_t)upp * 16);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(red + kTlWarps * Q * 32);
-  const int nslots = R / kBlk;
+  double *red = reinterpret_cast<double *>(msm + (size_t)upp * 16);          // [2][kTlWarps][Q][32]
+  uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * kTlWarps * Q * 32);  // [nslots]
+  uint64_t *empty = full + nslots;                                            // [nslots]
+  uint64_t *red_full = empty + nslots;                                        // [2]
+  uint64_t *red_empty = red_full + 2;                                         // [2]
 
   const long long a = blockIdx.x / split;
   const int p = (int)(blockIdx.x - a * split);
   const int e0 = p * upp * UE;
-  const int pe = min(D - e0, upp * UE);          // elements of this piece (> 0)
+  const int pe = min(D - e0, upp * UE);  // elements of this piece (> 0)
   const int punits = (pe + UE - 1) / UE;
   const uint32_t pbytes = (uint32_t)pe * sizeof(T);
+  const int nblk = (int)((F + kBlk - 1) / kBlk);
 
-  // multiplicities of this piece (zero padded), ring zeroed when the tail unit is partial
+  // prologue (all warps): multiplicities of this piece, zero padded; ring zeroed when rows are not
+  // 16-byte multiples (the tail unit is then partial and its padding must read as zero)
   for (int i = tid; i < upp * UE; i += kTlThreads)
     reinterpret_cast<T *>(msm)[i] = (i < pe) ? (mult ? mult[e0 + i] : (T)1) : (T)0;
   if (!bulk_ok) {
@@ -170,103 +230,107 @@ __global__ void __launch_bounds__(kTlThreads, 1)
     for (int i = tid; i < n16; i += kTlThreads) reinterpret_cast<int4 *>(ring)[i] = make_int4(0, 0, 0, 0);
   }
   if (tid == 0) {
-    for (int s = 0; s < nslots; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < nslots; ++s) {
+      mbar_init(&full[s], bulk_ok ? 1 : 32);
+      mbar_init(&empty[s], kTlWarps);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&red_full[i], kTlWarps);
+      mbar_init(&red_empty[i], 1);
+    }
     fence_mbar_init();
   }
   __syncthreads();
 
-  const size_t fstride = (size_t)A * D;  // elements between consecutive frames
-  const T *xa = X + (size_t)a * D + e0;
-  const int nblk = (int)((F + kBlk - 1) / kBlk);
-  double *srow = scratch + ((size_t)a * split + p) * Q * (size_t)F;
-  int issued = 0;
-
-  for (int b = 0; b < nblk; ++b) {
-    const int want = min(nblk - 1, b + ahead);
-    if (bulk_ok) {
-      if (warp == 0) {
-        // all warps passed the barrier that ended block b-1: the slots of blocks <= want are free
-        while (issued <= want) {
-          const long long f0 = (long long)issued * kBlk;
-          const int nf = (int)min((long long)kBlk, F - f0);
-          uint64_t *bar = &bars[issued % nslots];
-          if (lane == 0) mbar_expect_tx(bar, (uint32_t)nf * pbytes);
-          __syncwarp();
-          if (lane < nf) {
-            const long long f = f0 + lane;
-            bulk_g2s(ring + (size_t)(f % R) * stride, xa + (size_t)f * fstride, pbytes, bar);
-          }
-          ++issued;
+  if (warp == kTlWarps) {
+    // ===== producer ==========================================================================
+    const size_t fstride = (size_t)A * D;  // elements between consecutive frames
+    const T *xa = X + (size_t)a * D + e0;
+    const uint32_t ring_addr = smem_u32(ring);
+    for (int c = 0; c < nblk; ++c) {
+      // loading block c overwrites the frames of block c - nslots, last needed (as lag partners)
+      // by block j = c - nslots + lag_blocks: wait until the consumers are done with block j
+      const int j = c - nslots + lag_blocks;
+      if (j >= 0) mbar_wait(&empty[j % nslots], (uint32_t)((j / nslots) & 1));
+      const long long f0 = (long long)c * kBlk;
+      const int nf = (int)min((long long)kBlk, F - f0);
+      const int s = c % nslots;
+      if (bulk_ok) {
+        if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nf * pbytes);
+        __syncwarp();
+        if (lane < nf)
+          bulk_g2s(ring + (size_t)(s * kBlk + lane) * stride, xa + (size_t)(f0 + lane) * fstride, pbytes, &full[s]);
+      } else {
+        for (int fr = 0; fr < nf; ++fr) {
+          const T *src = xa + (size_t)(f0 + fr) * fstride;
+          const uint32_t dst = ring_addr + (uint32_t)(s * kBlk + fr) * stride;
+          for (int e = lane; e < pe; e += 32) cp_async_elem(dst + e * (uint32_t)sizeof(T), src + e, (int)sizeof(T));
         }
-      }
-      mbar_wait(&bars[b % nslots], (uint32_t)((b / nslots) & 1));
-    } else {
-      while (issued <= want) {  // unaligned rows: cooperative element-wise staging
-        const long long f0 = (long long)issued * kBlk;
-        const int nf = (int)min((long long)kBlk, F - f0);
-        for (int i = tid; i < nf * pe; i += kTlThreads) {
-          const int fr = i / pe, e = i - fr * pe;
-          const long long f = f0 + fr;
-          reinterpret_cast<T *>(ring + (size_t)(f % R) * stride)[e] = xa[(size_t)f * fstride + e];
-        }
-        ++issued;
-      }
-      __syncthreads();
-    }
-
-    // ---- compute: lane <-> frame fl ------------------------------------------------------
-    const long long fl = (long long)b * kBlk + lane;
-    const unsigned char *xb = ring + (size_t)(fl % R) * stride;
-    const unsigned char *yb[NW];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      long long fp = fl - win[k];
-      if (fp < 0) fp = fl;  // no partner yet: result unused, keep the address in range
-      yb[k] = ring + (size_t)(fp % R) * stride;
-    }
-    double acc[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) acc[q] = 0.0;
-
-    if constexpr (sizeof(T) == 8) {
-#pragma unroll 2
-      for (int u = warp; u < punits; u += kTlWarps) {
-        const double2 m = *reinterpret_cast<const double2 *>(msm + 16 * u);
-        const double2 x = *reinterpret_cast<const double2 *>(xb + 16 * u);
-        double2 y[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) y[k] = *reinterpret_cast<const double2 *>(yb[k] + 16 * u);
-        accum_unit<NW, EUCLID>(m, x, y, acc);
-      }
-    } else {
-      for (int u = warp; u < punits; u += 2 * kTlWarps) {
-        const int u2 = u + kTlWarps;
-        const bool two = u2 < punits;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 ma = *reinterpret_cast<const float4 *>(msm + 16 * u);
-        const float4 xa4 = *reinterpret_cast<const float4 *>(xb + 16 * u);
-        const float4 mb = two ? *reinterpret_cast<const float4 *>(msm + 16 * u2) : z;
-        const float4 xb4 = two ? *reinterpret_cast<const float4 *>(xb + 16 * u2) : z;
-        float4 ya[NW], yb4[NW];
-#pragma unroll
-        for (int k = 0; k < NW; ++k) {
-          ya[k] = *reinterpret_cast<const float4 *>(yb[k] + 16 * u);
-          yb4[k] = two ? *reinterpret_cast<const float4 *>(yb[k] + 16 * u2) : z;
-        }
-        accum_unit2<NW, EUCLID>(ma, xa4, ya, mb, xb4, yb4, acc);
+        cp_async_arrive_noinc(&full[s]);  // every lane: arrives once its own copies have landed
       }
     }
+  } else if (warp == kTlWarps + 1) {
+    // ===== reducer ===========================================================================
+    double *srow = scratch + ((size_t)a * split + p) * Q * (size_t)F;
+    for (int b = 0; b < nblk; ++b) {
+      const int i = b & 1;
+      mbar_wait(&red_full[i], (uint32_t)((b >> 1) & 1));
+      const double *r = red + (size_t)i * kTlWarps * Q * 32;
+      const long long fl = (long long)b * kBlk + lane;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) red[(warp * Q + q) * 32 + lane] = acc[q];
-    __syncthreads();
-    if (tid < Q * 32) {
-      const int q = tid >> 5;
-      double s = 0.0;
+      for (int q = 0; q < Q; ++q) {
+        double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < kTlWarps; ++w) s += red[(w * Q + q) * 32 + lane];
-      if (fl < F) srow[(size_t)q * F + fl] = s;
+        for (int w = 0; w < kTlWarps; ++w) s += r[(w * Q + q) * 32 + lane];
+        if (fl < F) srow[(size_t)q * F + fl] = s;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&red_empty[i]);
     }
-    __syncthreads();  // ends block b: ring slots older than max_lag and `red` may be reused
+  } else {
+    // ===== consumers: lane <-> frame ============================================================
+    const uint32_t ring_addr = smem_u32(ring), m_addr = smem_u32(msm);
+    const uint32_t ustep = 16u * kTlWarps;  // this warp's units are u = warp, warp + 8, ...
+    const uint32_t off0 = 16u * warp;
+    const int my_units = punits > warp ? (punits - warp + kTlWarps - 1) / kTlWarps : 0;
+    int wmod[NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) wmod[k] = win[k] % R;
+    for (int b = 0; b < nblk; ++b) {
+      const int s = b % nslots;
+      const int slot = s * kBlk + lane;  // ring slot of this lane's frame (R is a multiple of 32)
+      const uint32_t x_addr = ring_addr + (uint32_t)slot * stride;
+      uint32_t y_addr[NW];
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        int ys = slot - wmod[k];
+        if (ys < 0) ys += R;
+        y_addr[k] = ring_addr + (uint32_t)ys * stride;  // frames f < w read stale data: result unused
+      }
+      double acc[2 * Q];
+#pragma unroll
+      for (int q = 0; q < 2 * Q; ++q) acc[q] = 0.0;
+      mbar_wait(&full[s], (uint32_t)((b / nslots) & 1));
+      int n = 0;
+      for (; n + 4 <= my_units; n += 4)
+        accum_units<T, NW, 4, EUCLID>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+      if (n + 2 <= my_units) {
+        accum_units<T, NW, 2, EUCLID>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+        n += 2;
+      }
+      if (n < my_units) accum_units<T, NW, 1, EUCLID>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+      // hand the partial sums to the reducer
+      const int i = b & 1;
+      if (b >= 2) mbar_wait(&red_empty[i], (uint32_t)(((b >> 1) - 1) & 1));
+      double *r = red + ((size_t)i * kTlWarps + warp) * Q * 32;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) r[q * 32 + lane] = acc[2 * q] + acc[2 * q + 1];
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&red_full[i]);
+        mbar_arrive(&empty[s]);
+      }
+    }
   }
 }
 
@@ -342,7 +406,7 @@ static int launch_timelag(const void *X, const void *mult, double *scratch, int6
   ProfScope prof(SOAP_PROF_TIMELAG, s);
   kern<<<(unsigned)nblocks, kTlThreads, pl.smem, s>>>(static_cast<const T *>(X), static_cast<const T *>(mult),
                                                       scratch, (long long)F, (long long)A, D, pl.split, pl.upp,
-                                                      pl.stride, pl.R, pl.ahead, win4, bulk_ok);
+                                                      pl.stride, pl.R, (pl.max_lag + kBlk - 1) / kBlk, win4, bulk_ok);
   return check_launch("timelag_kernel");
 }
 

@@ -7,8 +7,10 @@ The reference itself returns 2e-8 instead of 0 (``SOAPdistanceNormalized(x, x)``
 
 * ``d**2`` (equivalently the kernel value ``k``) agrees to ``atol`` ABSOLUTE:
   1e-12 for the fp64 path, 1e-6 for the fp32 / 3xTF32 path (BASELINE.json north_star);
-* ``d`` agrees to the same number RELATIVE wherever ``d >= d_rel_min`` (0.1: the
-  cancellation has eaten < 2 digits there);
+* ``d`` agrees to the same number RELATIVE wherever ``d >= d_rel_min``: 0.1 for fp64 and 0.5
+  for the fp32 path (rel err of d = err(k) / d^2; an fp32 dot of O(1000) terms carries
+  err(k) ~ 2e-8 even with double accumulation of the 8-term fp32 chains, i.e. 2e-6 at d = 0.1
+  -- the reference's own float32 numpy path is less accurate than that);
 * NaNs: a NaN on either side is accepted only against NaN or against ``d**2 <= atol`` on the
   other side (both are "k rounded to just above / just below 1").
 """
@@ -17,7 +19,11 @@ import numpy as np
 TOL = {"f64": 1e-12, "f32": 1e-6}
 
 
-def assert_distance_parity(got, want, path="f64", d_rel_min=0.1, what=""):
+D_REL_MIN = {"f64": 0.1, "f32": 0.5}
+
+
+def assert_distance_parity(got, want, path="f64", d_rel_min=None, what=""):
+    d_rel_min = D_REL_MIN[path] if d_rel_min is None else d_rel_min
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
