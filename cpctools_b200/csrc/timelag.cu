@@ -27,7 +27,7 @@
 
 namespace soapb {
 
-constexpr int kTlWarps = 8;                      // consumer warps
+constexpr int kTlWarps = 12;                     // consumer warps (3 per SM sub-partition)
 constexpr int kTlThreads = (kTlWarps + 2) * 32;  // + producer warp + reducer warp
 constexpr int kBlk = 32;  // frames per block == lanes per warp
 
@@ -37,7 +37,7 @@ struct TimelagPlan {
 };
 
 static size_t tl_smem_bytes(int R, int stride, int upp, int Q) {
-  return (size_t)R * stride + (size_t)upp * 16 + (size_t)2 * kTlWarps * Q * 32 * 8 + (size_t)(2 * (R / kBlk) + 4) * 8 + 64;
+  return (size_t)R * stride + (size_t)upp * 16 + (size_t)kTlWarps * Q * 32 * 8 + (size_t)(2 * (R / kBlk) + 2) * 8 + 64;
 }
 
 static int env_int(const char *name, int dflt) {
@@ -186,13 +186,13 @@ __device__ __forceinline__ void accum_units(uint32_t m_addr, uint32_t x_addr, co
     accum_units_f32<NW, U, EUCLID>(m_addr, x_addr, y_addr, off, ustep, acc);
 }
 
-// Warp roles: warps 0..7 consume (lane = frame), warp 8 produces (TMA / cp.async), warp 9 reduces
-// the 8 consumers' partial sums of a block and writes them to scratch.  All hand-offs are
+// Warp roles: warps 0..11 consume (lane = frame), warp 12 produces (TMA / cp.async), warp 13 reduces
+// the consumers' partial sums of a block and writes them to scratch.  All hand-offs are
 // mbarriers; there is no __syncthreads after the prologue, so no warp ever convoys behind another.
 //   full[s]      producer -> consumers   block in ring slot-group s has landed
-//   empty[s]     consumers -> producer   block s consumed as "current" frames (8 arrivals)
-//   red_full[i]  consumers -> reducer    partial sums of a block are in red[i] (8 arrivals)
-//   red_empty[i] reducer -> consumers    red[i] may be overwritten
+//   empty[s]     consumers -> producer   block s consumed as "current" frames (one arrival per warp)
+//   red_full     consumers -> reducer    partial sums of a block are in red (one arrival per warp)
+//   red_empty    reducer -> consumers    red may be overwritten
 template <typename T, int NW, bool EUCLID>
 __global__ void __launch_bounds__(kTlThreads, 1)
     timelag_kernel(const T *__restrict__ X, const T *__restrict__ mult, double *__restrict__ scratch,
@@ -207,11 +207,11 @@ __global__ void __launch_bounds__(kTlThreads, 1)
 
   unsigned char *ring = smem_raw;
   unsigned char *msm = ring + (size_t)R * stride;
-  double *red = reinterpret_cast<double *>(msm + (size_t)upp * 16);          // [2][kTlWarps][Q][32]
-  uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * kTlWarps * Q * 32);  // [nslots]
-  uint64_t *empty = full + nslots;                                            // [nslots]
-  uint64_t *red_full = empty + nslots;                                        // [2]
-  uint64_t *red_empty = red_full + 2;                                         // [2]
+  double *red = reinterpret_cast<double *>(msm + (size_t)upp * 16);      // [kTlWarps][Q][32]
+  uint64_t *full = reinterpret_cast<uint64_t *>(red + kTlWarps * Q * 32);  // [nslots]
+  uint64_t *empty = full + nslots;                                        // [nslots]
+  uint64_t *red_full = empty + nslots;                                    // [1]
+  uint64_t *red_empty = red_full + 1;                                     // [1]
 
   const long long a = blockIdx.x / split;
   const int p = (int)(blockIdx.x - a * split);
@@ -234,10 +234,8 @@ __global__ void __launch_bounds__(kTlThreads, 1)
       mbar_init(&full[s], bulk_ok ? 1 : 32);
       mbar_init(&empty[s], kTlWarps);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&red_full[i], kTlWarps);
-      mbar_init(&red_empty[i], 1);
-    }
+    mbar_init(red_full, kTlWarps);
+    mbar_init(red_empty, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -273,9 +271,8 @@ __global__ void __launch_bounds__(kTlThreads, 1)
     // ===== reducer ===========================================================================
     double *srow = scratch + ((size_t)a * split + p) * Q * (size_t)F;
     for (int b = 0; b < nblk; ++b) {
-      const int i = b & 1;
-      mbar_wait(&red_full[i], (uint32_t)((b >> 1) & 1));
-      const double *r = red + (size_t)i * kTlWarps * Q * 32;
+      mbar_wait(red_full, (uint32_t)(b & 1));
+      const double *r = red;
       const long long fl = (long long)b * kBlk + lane;
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
@@ -285,12 +282,12 @@ __global__ void __launch_bounds__(kTlThreads, 1)
         if (fl < F) srow[(size_t)q * F + fl] = s;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&red_empty[i]);
+      if (lane == 0) mbar_arrive(red_empty);
     }
   } else {
     // ===== consumers: lane <-> frame ============================================================
     const uint32_t ring_addr = smem_u32(ring), m_addr = smem_u32(msm);
-    const uint32_t ustep = 16u * kTlWarps;  // this warp's units are u = warp, warp + 8, ...
+    const uint32_t ustep = 16u * kTlWarps;  // this warp's units are u = warp, warp + kTlWarps, ...
     const uint32_t off0 = 16u * warp;
     const int my_units = punits > warp ? (punits - warp + kTlWarps - 1) / kTlWarps : 0;
     int wmod[NW];
@@ -319,15 +316,14 @@ __global__ void __launch_bounds__(kTlThreads, 1)
         n += 2;
       }
       if (n < my_units) accum_units<T, NW, 1, EUCLID>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
-      // hand the partial sums to the reducer
-      const int i = b & 1;
-      if (b >= 2) mbar_wait(&red_empty[i], (uint32_t)(((b >> 1) - 1) & 1));
-      double *r = red + ((size_t)i * kTlWarps + warp) * Q * 32;
+      // hand the partial sums to the reducer (it is ~10x faster than a block: this wait is free)
+      if (b >= 1) mbar_wait(red_empty, (uint32_t)((b - 1) & 1));
+      double *r = red + (size_t)warp * Q * 32;
 #pragma unroll
       for (int q = 0; q < Q; ++q) r[q * 32 + lane] = acc[2 * q] + acc[2 * q + 1];
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&red_full[i]);
+        mbar_arrive(red_full);
         mbar_arrive(&empty[s]);
       }
     }
