@@ -152,8 +152,8 @@ static int launch_pairs_simt(const void *A, const void *B, void *out, int64_t M,
 
 static bool tensor_eligible(int64_t M, int64_t N, int D, int kind, int dtype) {
   if (kind == SOAP_KIND_EUCLID) return false;
-  if (dtype == SOAP_F64) return D % 4 == 0 && M >= 128 && N >= 128;
-  return D % 32 == 0 && M >= 256 && N >= 256;
+  if (dtype == SOAP_F64) return D % 2 == 0 && M >= 128 && N >= 128;
+  return M >= 128 && N >= 256;
 }
 
 }  // namespace soapb
@@ -182,8 +182,8 @@ extern "C" int soap_pairs(const void *data, const void *spectra, void *out, int6
   if (path == SOAP_PAIRS_TENSOR) {
     SOAP_REQUIRE(!am, "soap_pairs: argmin/min is only fused on the SIMT path");
     SOAP_REQUIRE(tensor_eligible(n_data, n_spectra, dim, kind, dtype),
-                 "soap_pairs: shape/kind not eligible for the tensor-core path (fp64: D%%4==0, >=128 rows; "
-                 "fp32: D%%32==0, >=256 rows; no EUCLID)");
+                 "soap_pairs: shape/kind not eligible for the tensor-core path (fp64: even D, >= 128 x 128; "
+                 "fp32: >= 128 x 256; no EUCLID)");
     tensor = true;
   } else if (path == SOAP_PAIRS_AUTO) {
     tensor = !am && scratch != nullptr && tensor_eligible(n_data, n_spectra, dim, kind, dtype) &&

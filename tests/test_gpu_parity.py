@@ -380,3 +380,76 @@ def test_properties_at_benchmark_row_sizes(S):
     periodic = raw[:5].repeat(12, 1, 1)
     (t5,) = timelag_device(periodic, (5,), _lib.KIND_SIMPLE, mult=mult)
     assert (t5 == 0).all()
+
+
+# ------------------------------------------------------------------ tensor-core all-pairs path
+@pytest.mark.parametrize("M,K,D", [(128, 128, 576), (300, 257, 576), (513, 140, 1728), (200, 333, 50)])
+def test_pairs_tensor_fp64_vs_oracle(S, M, K, D):
+    """fp64 all-pairs through the DMMA (FP64 tensor-core) GEMM path: same rule as every fp64 path."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.classify import pairs_device
+
+    rng = np.random.default_rng(M * 7 + K)
+    a, b = rng.random((M, D)), rng.random((K, D))
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    for name, (fn, kind, power) in _kinds(S).items():
+        if name == "normalized":
+            sa, sb = O.normalizeArray(a), O.normalizeArray(b)
+            xa, xb = torch.from_numpy(sa).cuda(), torch.from_numpy(sb).cuda()
+        else:
+            sa, sb, xa, xb = a, b, ta, tb
+        want = O.getDistanceBetween_batched(sa, sb, kind, power)
+        lib_kind = {"simple": _lib.KIND_SIMPLE, "kernel1": _lib.KIND_KERNEL, "kernel2": _lib.KIND_KERNEL, "normalized": _lib.KIND_NORMALIZED}[name]
+        got = pairs_device(xa, xb, lib_kind, power, path=_lib.PAIRS_TENSOR).cpu().numpy()
+        assert_distance_parity(got, want, "f64", what=f"tensor {name}")
+        simt = pairs_device(xa, xb, lib_kind, power, path=_lib.PAIRS_SIMT).cpu().numpy()
+        assert_distance_parity(got, simt, "f64", what=f"tensor vs simt {name}")
+
+
+def test_pairs_tensor_self_distance_and_symmetry(S):
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.classify import pairs_device
+
+    X = torch.nn.functional.normalize(torch.rand(700, 576, dtype=torch.float64, device="cuda"), dim=-1)
+    d = pairs_device(X, X, _lib.KIND_NORMALIZED, 1, path=_lib.PAIRS_TENSOR)
+    assert torch.equal(d, d.T)  # x.y and y.x are summed in the same order
+    assert (torch.diagonal(d) <= 1.0e-7).all()  # SURVEY appendix A.9: a few 1e-8, never NaN
+    ds = pairs_device(X, X, _lib.KIND_SIMPLE, 1, path=_lib.PAIRS_TENSOR)
+    assert (torch.diagonal(ds) <= 1.0e-7).all() and not torch.isnan(ds).any()
+
+
+@pytest.mark.parametrize("M,K,D", [(128, 256, 576), (300, 600, 576), (517, 333, 1728), (1000, 1031, 50)])
+def test_pairs_tensor_fp32_3xtf32_vs_oracle(S, M, K, D):
+    """fp32 all-pairs through the tcgen05 3xTF32 path against the fp64 oracle of the same float32
+    inputs: d^2 to 1e-6 absolute, d to 1e-6 relative where d >= 0.5 (the fp32-path rule)."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.classify import pairs_device
+
+    rng = np.random.default_rng(M + 3 * K)
+    a = rng.random((M, D)).astype(np.float32)
+    b = rng.random((K, D)).astype(np.float32)
+    an = (a / np.linalg.norm(a, axis=-1, keepdims=True)).astype(np.float32)
+    bn = (b / np.linalg.norm(b, axis=-1, keepdims=True)).astype(np.float32)
+    for name, (fn, kind, power) in _kinds(S).items():
+        sa, sb = (an, bn) if name == "normalized" else (a, b)
+        want = O.getDistanceBetween_batched(sa.astype(np.float64), sb.astype(np.float64), kind, power)
+        lib_kind = {"simple": _lib.KIND_SIMPLE, "kernel1": _lib.KIND_KERNEL, "kernel2": _lib.KIND_KERNEL, "normalized": _lib.KIND_NORMALIZED}[name]
+        got = pairs_device(torch.from_numpy(sa).cuda(), torch.from_numpy(sb).cuda(), lib_kind, power, path=_lib.PAIRS_TENSOR)
+        assert got.dtype == torch.float32
+        assert_distance_parity(got.cpu().numpy(), want, "f32", what=f"3xtf32 {name}")
+
+
+def test_pairs_tensor_fp32_many_tiles_persistent(S):
+    """more tiles than SMs (persistent loop, both TMEM accumulator stages, ragged edges)."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.classify import pairs_device
+
+    X = torch.nn.functional.normalize(torch.rand(2900, 576, dtype=torch.float32, device="cuda"), dim=-1)
+    Y = torch.nn.functional.normalize(torch.rand(3700, 576, dtype=torch.float32, device="cuda"), dim=-1)
+    got = pairs_device(X, Y, _lib.KIND_NORMALIZED, 1, path=_lib.PAIRS_TENSOR)
+    want = torch.sqrt(torch.abs(2.0 - 2.0 * (X.double() @ Y.double().T)))
+    assert_distance_parity(got.cpu().numpy(), want.cpu().numpy(), "f32", what="3xtf32 persistent")
