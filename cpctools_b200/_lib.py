@@ -16,7 +16,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libsoapb200.so")
-SOURCES = ("capi.cu", "expand.cu", "timelag.cu", "pairs.cu", "pairs_dmma.cu", "pairs_tf32.cu")
+SOURCES = ("capi.cu", "expand.cu", "timelag.cu", "pairs.cu", "pairs_dmma.cu", "pairs_tf32.cu", "pairs_i8.cu")
 NVCC_FLAGS = (
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--threads", "0",
@@ -25,7 +25,7 @@ NVCC_FLAGS = (
 # dtype / kind / path codes of include/soap_b200.h
 F32, F64 = 0, 1
 KIND_SIMPLE, KIND_KERNEL, KIND_NORMALIZED, KIND_DOT, KIND_COSCLIP, KIND_EUCLID, KIND_NORMALIZED_FUSED = range(7)
-PAIRS_AUTO, PAIRS_SIMT, PAIRS_TENSOR = 0, 1, 2
+PAIRS_AUTO, PAIRS_SIMT, PAIRS_TENSOR, PAIRS_TENSOR_NATIVE = 0, 1, 2, 3
 MAX_WINDOWS = 4
 
 # every symbol include/soap_b200.h declares: name -> (restype, argtypes)
@@ -58,6 +58,7 @@ def _needs_rebuild() -> bool:
     built = os.path.getmtime(LIB_PATH)
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [
         os.path.join(CSRC, "common.cuh"),
+        os.path.join(CSRC, "tc05.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "soap_b200.h"),
     ]
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))

@@ -8,7 +8,8 @@
 // This SIMT path serves every shape and every distance kind (row norms are accumulated in the
 // same pass, so nothing is pre-normalised or staged): it is the path of the classification
 // row (few references: memory-bound GEMV-like) and of small matrices.  Large all-pairs matrices
-// go to the tensor-core kernels (pairs_dmma.cu for fp64, pairs_tf32.cu for fp32).
+// go to the tensor-core kernels: pairs_i8.cu (tcgen05 INT8, exact digit-split accumulation, both
+// dtypes) by default; pairs_dmma.cu (fp64 DMMA) and pairs_tf32.cu (3xTF32) as the native-format paths.
 #include "common.cuh"
 
 namespace soapb {
@@ -19,6 +20,11 @@ size_t pairs_dmma_scratch(int64_t M, int64_t N, int D);
 int pairs_tf32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                int power, void *scratch, cudaStream_t s);
 size_t pairs_tf32_scratch(int64_t M, int64_t N, int D);
+int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
+                 int power, void *scratch, cudaStream_t s);
+int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
+                 int power, void *scratch, cudaStream_t s);
+size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype);
 
 constexpr int kPT = 64;   // tile edge
 constexpr int kPK = 16;   // k-slab
@@ -150,9 +156,9 @@ static int launch_pairs_simt(const void *A, const void *B, void *out, int64_t M,
   return check_launch("pairs_simt_kernel");
 }
 
-static bool tensor_eligible(int64_t M, int64_t N, int D, int kind, int dtype) {
+static bool tensor_eligible(int64_t M, int64_t N, int D, int kind, int dtype, int path) {
   if (kind == SOAP_KIND_EUCLID) return false;
-  if (dtype == SOAP_F64) return D % 2 == 0 && M >= 128 && N >= 128;
+  if (path == SOAP_PAIRS_TENSOR_NATIVE && dtype == SOAP_F64) return D % 2 == 0 && M >= 128 && N >= 128;
   return M >= 128 && N >= 256;
 }
 
@@ -162,8 +168,9 @@ using namespace soapb;
 
 extern "C" size_t soap_pairs_scratch_bytes(int64_t n_data, int64_t n_spectra, int dim, int dtype, int path) {
   if (path == SOAP_PAIRS_SIMT) return 0;
-  if (dtype == SOAP_F64) return pairs_dmma_scratch(n_data, n_spectra, dim);
-  return pairs_tf32_scratch(n_data, n_spectra, dim);
+  if (path == SOAP_PAIRS_TENSOR_NATIVE)
+    return dtype == SOAP_F64 ? pairs_dmma_scratch(n_data, n_spectra, dim) : pairs_tf32_scratch(n_data, n_spectra, dim);
+  return pairs_i8_scratch(n_data, n_spectra, dim, dtype);
 }
 
 extern "C" int soap_pairs(const void *data, const void *spectra, void *out, int64_t n_data, int64_t n_spectra,
@@ -179,23 +186,31 @@ extern "C" int soap_pairs(const void *data, const void *spectra, void *out, int6
   auto s = static_cast<cudaStream_t>(stream);
   const bool am = argmin_out || min_out;
   bool tensor = false;
-  if (path == SOAP_PAIRS_TENSOR) {
+  if (path == SOAP_PAIRS_TENSOR || path == SOAP_PAIRS_TENSOR_NATIVE) {
     SOAP_REQUIRE(!am, "soap_pairs: argmin/min is only fused on the SIMT path");
-    SOAP_REQUIRE(tensor_eligible(n_data, n_spectra, dim, kind, dtype),
-                 "soap_pairs: shape/kind not eligible for the tensor-core path (fp64: even D, >= 128 x 128; "
-                 "fp32: >= 128 x 256; no EUCLID)");
+    SOAP_REQUIRE(tensor_eligible(n_data, n_spectra, dim, kind, dtype, path),
+                 "soap_pairs: shape/kind not eligible for the tensor-core path (>= 128 x 256; native fp64: even D, "
+                 ">= 128 x 128; no EUCLID)");
     tensor = true;
   } else if (path == SOAP_PAIRS_AUTO) {
-    tensor = !am && scratch != nullptr && tensor_eligible(n_data, n_spectra, dim, kind, dtype) &&
+    tensor = !am && scratch != nullptr && tensor_eligible(n_data, n_spectra, dim, kind, dtype, SOAP_PAIRS_TENSOR) &&
              (double)n_data * (double)n_spectra >= 1.0e6;
   }
+  if (tensor && path == SOAP_PAIRS_AUTO) path = SOAP_PAIRS_TENSOR;
   if (tensor) {
     SOAP_REQUIRE(scratch != nullptr, "soap_pairs: the tensor-core path needs soap_pairs_scratch_bytes() of scratch");
+    if (path == SOAP_PAIRS_TENSOR_NATIVE) {
+      if (dtype == SOAP_F64)
+        return pairs_dmma(static_cast<const double *>(data), static_cast<const double *>(spectra),
+                          static_cast<double *>(out), n_data, n_spectra, dim, ldo, kind, power, scratch, s);
+      return pairs_tf32(static_cast<const float *>(data), static_cast<const float *>(spectra),
+                        static_cast<float *>(out), n_data, n_spectra, dim, ldo, kind, power, scratch, s);
+    }
     if (dtype == SOAP_F64)
-      return pairs_dmma(static_cast<const double *>(data), static_cast<const double *>(spectra),
-                        static_cast<double *>(out), n_data, n_spectra, dim, ldo, kind, power, scratch, s);
-    return pairs_tf32(static_cast<const float *>(data), static_cast<const float *>(spectra),
-                      static_cast<float *>(out), n_data, n_spectra, dim, ldo, kind, power, scratch, s);
+      return pairs_i8_f64(static_cast<const double *>(data), static_cast<const double *>(spectra),
+                          static_cast<double *>(out), n_data, n_spectra, dim, ldo, kind, power, scratch, s);
+    return pairs_i8_f32(static_cast<const float *>(data), static_cast<const float *>(spectra),
+                        static_cast<float *>(out), n_data, n_spectra, dim, ldo, kind, power, scratch, s);
   }
   if (dtype == SOAP_F64)
     return launch_pairs_simt<double>(data, spectra, out, n_data, n_spectra, dim, ldo, kind, power, argmin_out,

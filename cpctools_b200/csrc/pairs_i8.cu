@@ -1,0 +1,347 @@
+// pairs_i8.cu -- K5: the all-pairs SOAP distance matrix on the tcgen05 INT8 tensor cores with EXACT
+// accumulation (Ozaki-style digit splitting), the distance as the GEMM epilogue.
+//
+// Reference semantics: getDistanceBetween (src/SOAPify/classify.py:96-117) with one of the distances
+// of src/SOAPify/distances.py; output dtype = data.dtype (classify.py:113).
+//
+// Why not 3xTF32: the TMEM accumulator of tcgen05.mma.kind::tf32 adds every K=8 slice with fp32
+// round-toward-zero, a one-sided bias of ~0.5 ulp per slice; over K = 576 x 3 passes it reaches
+// 6e-6 on the kernel value (measured, pairs_tf32.cu), above the 1e-6 tolerance of the fp32 path.
+// Integer accumulation has no rounding at all:
+//   every row is scaled by sigma_i = max|x_i| / (126.5 * 2^(8(ND-1))) and rounded to an integer
+//   X = sum_a d_a 2^(8(ND-1-a)) with ND balanced base-256 digits d_a in [-128,127] (int8 planes);
+//   x.y = sigma_i sigma_j sum_{a,b} 2^(8(2ND-2-a-b)) (d_a . d_b); the digit products d_a.d_b are
+//   int8 x int8 -> int32 tensor-core GEMMs, EXACT (|sum| <= 6 x 576 x 2^14 << 2^31); pairs with
+//   a+b > ND-1 are dropped (relative weight <= 2^(-8 ND)), pairs of equal a+b share one accumulator.
+//   ND = 3 (24-bit digits) for float32 data: 6 passes, error ~2^-24 of max|x|max|y| per product;
+//   ND = 6 (48-bit digits) for float64 data: 21 passes, error ~2^-48: fp64 accuracy at >4x the
+//   throughput of the FP64 (DMMA) tensor path.
+//
+// One persistent CTA per SM, warp specialised like pairs_tf32.cu: warp 0 TMA producer (2 tensor maps
+// over the stacked digit planes, swizzled K-major tiles), warp 1 issues tcgen05.mma.kind::i8
+// (M128 x BN x K32 per instruction, ND(ND+1)/2 passes per K step into ND TMEM accumulators),
+// warps 2..9 drain TMEM (tcgen05.ld), recombine the digit sums, apply the distance and store.
+#include "tc05.cuh"
+
+namespace soapb {
+
+constexpr int kI8BM = 128;
+constexpr int kI8EpiWarps = 8;                       // two per TMEM lane quarter: latency hiding in the epilogue
+constexpr int kI8Threads = 64 + 32 * kI8EpiWarps;
+constexpr int kI8Stages = 2;
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- pre-pass: row scale, digit planes (zero padded to Dp), squared row norms ----------------------
+// planes[a][row][k] int8; scale[row] = sigma * 2^(8(ND-1)) so that  x.y = scale_i scale_j sum_g S_g 2^(-8g)
+template <typename T, int ND>
+__global__ void __launch_bounds__(256)
+    ozaki_split_kernel(const T *__restrict__ X, int8_t *__restrict__ planes, double *__restrict__ scale,
+                       double *__restrict__ norm2, long long rows, int D, int Dp) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T *x = X + (size_t)row * D;
+  double mx = 0.0, acc = 0.0;
+  for (int k = lane; k < D; k += 32) {
+    const double v = (double)x[k];
+    mx = fmax(mx, fabs(v));
+    acc = fma(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  acc = warp_sum(acc);
+  const double cap = 126.5 * (double)(1ull << (8 * (ND - 1)));
+  const bool finite = (acc == acc) && (acc < 1.0e308);
+  const double sigma = (mx > 0.0 && finite) ? mx / cap : 1.0;
+  const double inv = 1.0 / sigma;
+  if (lane == 0) {
+    scale[row] = finite ? sigma * (double)(1ull << (8 * (ND - 1))) : __longlong_as_double(0x7ff8000000000000ll);
+    norm2[row] = acc;
+  }
+  const size_t plane_stride = (size_t)rows * Dp;
+  for (int k0 = 4 * lane; k0 < Dp; k0 += 128) {
+    int8_t dig[ND][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + e;
+      long long v = 0;
+      if (k < D && finite) v = __double2ll_rn((double)x[k] * inv);
+      // balanced base-256 digits, least significant first with carry: v == sum_a dig[a] 256^(ND-1-a)
+#pragma unroll
+      for (int a = ND - 1; a >= 0; --a) {
+        int d = (int)(v & 0xff);
+        if (d > 127) d -= 256;
+        dig[a][e] = (int8_t)d;
+        v = (v - d) >> 8;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < ND; ++a) {
+      char4 c = make_char4(dig[a][0], dig[a][1], dig[a][2], dig[a][3]);
+      *reinterpret_cast<char4 *>(planes + a * plane_stride + (size_t)row * Dp + k0) = c;
+    }
+  }
+}
+
+__device__ __forceinline__ void tile_coords_i8(long long t, int tiles_m, int tiles_n, int &tm, int &tn) {
+  constexpr int PW = 6;
+  const long long per_panel = (long long)PW * tiles_m;
+  const int panel = (int)(t / per_panel);
+  const int first = panel * PW;
+  const int width = min(PW, tiles_n - first);
+  const long long r = t - (long long)panel * per_panel;
+  tm = (int)(r / width);
+  tn = first + (int)(r % width);
+}
+
+template <int ND, int BN, int BKB, typename OutT>
+__global__ void __launch_bounds__(kI8Threads, 1)
+    pairs_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    OutT *__restrict__ out, const double *__restrict__ sa, const double *__restrict__ sb,
+                    const double *__restrict__ uu, const double *__restrict__ vv, long long M, long long N, int KB,
+                    long long ldo, int kind, int power, int tiles_m, int tiles_n) {
+  constexpr int BM = kI8BM, STAGES = kI8Stages;
+  constexpr int A_PLANE = BM * BKB, B_PLANE = BN * BKB;
+  constexpr int STAGE_BYTES = ND * (A_PLANE + B_PLANE);
+  constexpr int KS = BKB / 32;  // UMMA K = 32 for 8-bit operands
+  // instruction descriptor: D = s32, A = B = signed int8, K-major, N = BN, M = 128
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  static_assert(ND * BN <= 512, "accumulators exceed TMEM");
+  static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t *full = bars, *empty = bars + STAGES;
+  uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = tmem_full + 1;
+  uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tiles = (long long)tiles_m * tiles_n;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, kI8EpiWarps);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: digit plane a of the operand lives at rows [a*rows, (a+1)*rows) ==========
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        int tm, tn;
+        tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait_guard(&empty[s], ph ^ 1);
+          unsigned char *st = smem + (size_t)s * STAGE_BYTES;
+          mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+#pragma unroll
+          for (int a = 0; a < ND; ++a) {
+            tma_load_2d(st + a * A_PLANE, &map_a, kb * BKB, (int)(a * M + (long long)tm * BM), &full[s]);
+            tma_load_2d(st + ND * A_PLANE + a * B_PLANE, &map_b, kb * BKB, (int)(a * N + (long long)tn * BN), &full[s]);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ===========================================================================
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      mbar_wait_guard(tmem_empty, (uint32_t)((it & 1) ^ 1));  // epilogue has drained the previous tile
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait_guard(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+              const uint32_t pa = st + a * A_PLANE;
+              const uint64_t da = (BKB == 128 ? umma_desc_sw128(pa) : umma_desc_sw64(pa)) + adv;
+#pragma unroll
+              for (int b = 0; b < ND - a; ++b) {
+                const uint32_t pb = st + ND * A_PLANE + b * B_PLANE;
+                const uint64_t db = (BKB == 128 ? umma_desc_sw128(pb) : umma_desc_sw64(pb)) + adv;
+                // digit pairs of equal weight a+b share accumulator g = a+b; (0, g) is its first pass
+                tc_mma_i8(tmem_base + (uint32_t)((a + b) * BN), da, db, IDESC, (kb | ks | a) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          tc_commit(&empty[s]);
+          if (kb == KB - 1) tc_commit(tmem_full);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue warps (TMEM lane quarter = warp % 4) ===========================================
+    const int q = warp & 3;               // TMEM lane quarter this warp may read
+    const int part = (warp - 2) >> 2;      // column chunks are interleaved over the warps of a quarter
+    constexpr int PARTS = kI8EpiWarps / 4;
+    const bool need_norms = (kind != SOAP_KIND_NORMALIZED);
+    constexpr int VEC = 16 / (int)sizeof(OutT);
+    const bool vec_ok = ((ldo % VEC) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    int it = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      int tm, tn;
+      tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
+      mbar_wait_guard(tmem_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      const long long row = (long long)tm * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const double si = row_ok ? sa[row] : 0.0;
+      const double ui = (need_norms && row_ok) ? uu[row] : 1.0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = part; c < BN / 16; c += PARTS) {
+        uint32_t v[ND][16];
+#pragma unroll
+        for (int g = 0; g < ND; ++g) tmem_ld16(taddr + (uint32_t)(g * BN + c * 16), v[g]);
+        tmem_ld_wait();
+        const long long col0 = (long long)tn * BN + c * 16;
+        if (row_ok && col0 < N) {
+          OutT r[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const long long col = col0 + j;
+            const bool col_ok = col < N;
+            double tsum;
+            if constexpr (ND <= 3) {
+              long long acc = 0;  // exact: |acc| < 2^45
+#pragma unroll
+              for (int g = 0; g < ND; ++g) acc = acc * 256 + (long long)(int)v[g][j];
+              tsum = (double)acc * (1.0 / (double)(1ull << (8 * (ND - 1))));
+            } else {
+              tsum = (double)(int)v[ND - 1][j];
+#pragma unroll
+              for (int g = ND - 2; g >= 0; --g) tsum = fma(tsum, 1.0 / 256.0, (double)(int)v[g][j]);
+            }
+            const double gdot = si * (col_ok ? sb[col] : 0.0) * tsum;
+            if constexpr (sizeof(OutT) == 4) {
+              if (!need_norms) {
+                r[j] = sqrtf(fabsf(2.0f - 2.0f * (float)gdot));  // SOAPdistanceNormalized in float32
+              } else {
+                r[j] = (OutT)soap_epilogue(gdot, ui, col_ok ? vv[col] : 1.0, kind, power);
+              }
+            } else {
+              r[j] = (OutT)soap_epilogue(gdot, ui, (need_norms && col_ok) ? vv[col] : 1.0, kind, power);
+            }
+          }
+          OutT *dst = out + (size_t)row * ldo + col0;
+          if (vec_ok && col0 + 16 <= N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += VEC) *reinterpret_cast<int4 *>(dst + j) = *reinterpret_cast<const int4 *>(&r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j < N) dst[j] = r[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+template <int ND, int BKB>
+static size_t i8_scratch_bytes(int64_t M, int64_t N, int D) {
+  const size_t Dp = align_up((size_t)D, BKB);
+  return align_up((size_t)ND * M * Dp, 1024) + align_up((size_t)ND * N * Dp, 1024) + (size_t)(M + N) * 16 + 4096;
+}
+
+template <typename InT, int ND, int BN, int BKB, typename OutT>
+static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
+                           int power, void *scratch, cudaStream_t s) {
+  SOAP_REQUIRE(out != nullptr, "soap_pairs: the tensor-core path writes the full matrix (out == NULL)");
+  SOAP_REQUIRE((int64_t)ND * M < 2147483647LL && (int64_t)ND * N < 2147483647LL, "soap_pairs: too many rows for one call");
+  const int Dp = (int)align_up((size_t)D, BKB);
+  unsigned char *p = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<uintptr_t>(scratch), 1024));
+  const bool same = (static_cast<const void *>(A) == static_cast<const void *>(B) && M == N);
+  int8_t *pa = reinterpret_cast<int8_t *>(p);
+  p += align_up((size_t)ND * M * Dp, 1024);
+  int8_t *pb = pa;
+  if (!same) {
+    pb = reinterpret_cast<int8_t *>(p);
+    p += align_up((size_t)ND * N * Dp, 1024);
+  }
+  double *sa = reinterpret_cast<double *>(p);
+  double *ua = sa + M;
+  double *sb = same ? sa : ua + M;
+  double *ub = same ? ua : sb + N;
+  ozaki_split_kernel<InT, ND><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(A, pa, sa, ua, M, D, Dp);
+  int rc = check_launch("ozaki_split_kernel");
+  if (rc) return rc;
+  if (!same) {
+    ozaki_split_kernel<InT, ND><<<(unsigned)((N + 7) / 8), 256, 0, s>>>(B, pb, sb, ub, N, D, Dp);
+    if ((rc = check_launch("ozaki_split_kernel"))) return rc;
+  }
+  const CUtensorMapSwizzle swz = BKB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap map_a, map_b;
+  if ((rc = make_tensor_map_2d(&map_a, pa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * M, Dp, BKB, kI8BM, swz))) return rc;
+  if ((rc = make_tensor_map_2d(&map_b, pb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * N, Dp, BKB, BN, swz))) return rc;
+  const int tiles_m = (int)((M + kI8BM - 1) / kI8BM), tiles_n = (int)((N + BN - 1) / BN);
+  const long long tiles = (long long)tiles_m * tiles_n;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  constexpr size_t SMEM = 1024 + (size_t)kI8Stages * ND * (kI8BM + BN) * BKB + 256;
+  auto kern = pairs_i8_kernel<ND, BN, BKB, OutT>;
+  SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+  ProfScope prof(SOAP_PROF_PAIRS, s);
+  kern<<<grid, kI8Threads, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n);
+  return check_launch("pairs_i8_kernel");
+}
+
+size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
+  return dtype == SOAP_F64 ? i8_scratch_bytes<6, 64>(M, N, D) : i8_scratch_bytes<3, 128>(M, N, D);
+}
+
+int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
+                 int power, void *scratch, cudaStream_t s) {
+  return launch_pairs_i8<float, 3, 160, 128, float>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
+}
+
+int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
+                 int power, void *scratch, cudaStream_t s) {
+  return launch_pairs_i8<double, 6, 80, 64, double>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
+}
+
+}  // namespace soapb

@@ -109,11 +109,14 @@ int soap_diff_transposed(const double *t, double *dt, int64_t rows, int64_t n_at
  * out[i][j] = dist(data[i], spectra[j]); data[n_data][D], spectra[n_spectra][D] (dtype);
  * out has leading dimension ldo (elements) and the type of `dtype` (classify.py:113).
  * path: SOAP_PAIRS_AUTO picks; SOAP_PAIRS_SIMT = CUDA-core tiles (any size);
- * SOAP_PAIRS_TENSOR = tensor-core GEMM (fp64: DMMA m8n8k4; fp32: tcgen05 3xTF32).
+ * SOAP_PAIRS_TENSOR = tcgen05 INT8 tensor-core GEMM with exact digit-split accumulation (3 int8
+ * digits for fp32 data, 6 for fp64: fp32 / fp64 accuracy respectively);
+ * SOAP_PAIRS_TENSOR_NATIVE = native-format tensor GEMM (fp64: DMMA; fp32: tcgen05 3xTF32, whose
+ * fp32 round-toward-zero accumulation limits it to ~2e-5 on d^2).
  * If argmin_out / min_out are non-NULL the row-wise argmin (int32) / min (double) over j is
  * produced as well (applyClassification, classify.py:274-275) and `out` may be NULL.
  */
-enum { SOAP_PAIRS_AUTO = 0, SOAP_PAIRS_SIMT = 1, SOAP_PAIRS_TENSOR = 2 };
+enum { SOAP_PAIRS_AUTO = 0, SOAP_PAIRS_SIMT = 1, SOAP_PAIRS_TENSOR = 2, SOAP_PAIRS_TENSOR_NATIVE = 3 };
 size_t soap_pairs_scratch_bytes(int64_t n_data, int64_t n_spectra, int dim, int dtype, int path);
 int soap_pairs(const void *data, const void *spectra, void *out, int64_t n_data, int64_t n_spectra,
                int dim, int64_t ldo, int kind, int power, int dtype, int path, int32_t *argmin_out,

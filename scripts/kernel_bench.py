@@ -122,7 +122,7 @@ def main():
         N = 8192 if args.quick else 25000
         for dt, code in ((torch.float64, _lib.F64), (torch.float32, _lib.F32)):
             X = torch.nn.functional.normalize(fill((N, 576), dt), dim=-1)
-            for path, pname in ((_lib.PAIRS_SIMT, "simt"), (_lib.PAIRS_TENSOR, "tensor")):
+            for path, pname in ((_lib.PAIRS_SIMT, "simt"), (_lib.PAIRS_TENSOR_NATIVE, "tensor-native"), (_lib.PAIRS_TENSOR, "tensor-int8")):
                 out = torch.empty((N, N), dtype=dt, device="cuda")
                 try:
                     fn = lambda: pairs_device(X, X, _lib.KIND_NORMALIZED, 1, path=path, out=out)
