@@ -1,0 +1,112 @@
+"""Multi-GPU sharding of the hot path: one process per GPU (``torch.distributed``, NCCL over NVLink).
+
+Every part of the path shards without a data-path exchange:
+
+* expand / normalise / timeSOAP: every atom's time series is independent -> contiguous ATOM
+  ranges per rank (no halo); results stay sharded or are gathered once at the end
+  (``all_gather`` of ``[F-w, A/G]`` slabs, a few hundred MB at most);
+* all-pairs matrix: the (small) vector set is replicated, each rank computes a ROW BLOCK of the
+  output, which stays sharded (it does not fit one GPU at the benchmark size); only reductions
+  (row minima / arg-minima, checksums) are gathered.
+
+The collectives only move results.  The functions below take the per-shard computation as a
+callable so that the partition / gather logic is testable on CPU with the gloo backend.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def _world(group=None):
+    if dist is None or not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def shard_range(n: int, rank: int, world: int) -> slice:
+    """Contiguous, balanced partition of ``range(n)``: the first ``n % world`` ranks get one extra."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return slice(lo, lo + base + (1 if rank < extra else 0))
+
+
+def atom_shard(n_atoms: int, group=None) -> slice:
+    rank, world = _world(group)
+    return shard_range(n_atoms, rank, world)
+
+
+def gather_columns(local, n_total: int, group=None):
+    """All-gather ``[rows, n_local]`` slabs that partition the LAST axis by :func:`shard_range` into
+    the full ``[rows, n_total]`` tensor on every rank (slabs are padded to the largest shard)."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    widest = shard_range(n_total, 0, world)
+    width = widest.stop - widest.start
+    padded = local.new_zeros(local.shape[:-1] + (width,))
+    padded[..., : local.shape[-1]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    out = []
+    for r, p in enumerate(parts):
+        s = shard_range(n_total, r, world)
+        out.append(p[..., : s.stop - s.start])
+    return torch.cat(out, dim=-1)
+
+
+def gather_rows(local, n_total: int, group=None):
+    """Same as :func:`gather_columns` for a partition of the FIRST axis."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    moved = local.movedim(0, -1)
+    return gather_columns(moved, n_total, group).movedim(-1, 0).contiguous()
+
+
+def time_soap_sharded(trajectory, windows: Sequence[int], compute: Callable, n_atoms_total: int = None,
+                      gather: bool = True, group=None):
+    """timeSOAP over an atom-sharded trajectory.
+
+    ``trajectory`` is this rank's ``[F, A_local, D]`` slab (its :func:`atom_shard` of the atoms);
+    ``compute(trajectory, windows)`` returns one ``[F-w, A_local]`` tensor per window (e.g.
+    ``cpctools_b200.analysis.timelag_device`` bound to a distance).  With ``gather`` the slabs are
+    all-gathered into ``[F-w, A]`` on every rank; the derivative is taken AFTER the gather by the
+    caller (or before, per shard: ``diff`` acts along frames, so both orders agree)."""
+    local = compute(trajectory, windows)
+    if not gather:
+        return local
+    rank, world = _world(group)
+    if n_atoms_total is None:
+        counts = torch.tensor([trajectory.shape[1]], dtype=torch.int64, device=local[0].device)
+        if world > 1:
+            dist.all_reduce(counts, group=group)
+        n_atoms_total = int(counts.item())
+    return [gather_columns(t, n_atoms_total, group) for t in local]
+
+
+def all_pairs_row_block(vectors, compute: Callable, group=None):
+    """Row-block sharded all-pairs matrix: rank r computes ``compute(vectors[rows_r], vectors)``
+    (``[n_r, N]``, kept on the rank) and the row-wise minimum over OTHER vectors, its arg-minimum
+    and a checksum, which ARE gathered.  Returns ``(block, rows, row_min[N], row_argmin[N], checksum)``."""
+    rank, world = _world(group)
+    n = int(vectors.shape[0])
+    rows = shard_range(n, rank, world)
+    block = compute(vectors[rows], vectors)
+    masked = block.clone()
+    idx = torch.arange(rows.start, rows.stop, device=block.device)
+    masked[torch.arange(idx.numel(), device=block.device), idx] = float("inf")  # drop the self distance
+    masked = torch.nan_to_num(masked, nan=float("inf"))
+    local_min, local_arg = masked.min(dim=1)
+    row_min = gather_rows(local_min, n, group)
+    row_arg = gather_rows(local_arg, n, group)
+    checksum = torch.nan_to_num(block.double(), nan=0.0).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(checksum, group=group)
+    return block, rows, row_min, row_arg, float(checksum.item())
