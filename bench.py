@@ -253,9 +253,15 @@ def run_gpu_arm(args):
     algo_bytes = frames * atoms * dc * 8 + sum((frames - w) * atoms * 8 for w in WINDOWS)
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_timelag_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read+write of one `ncu --set full` capture, scaled by the atom count
+        tj = json.load(open(tpath))
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * atoms / tj["atoms"] * frames / 1000
+        traffic_src = f"{tj['capture']} ({tj['config']}), scaled linearly to this tile"
     roofline = {
         "bound": "hbm", "kernel": "timelag_kernel<double,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": k_ms,
         "kernel_share_of_step": k_ms * len(kernel_ms) / (ev[0].elapsed_time(ev[-1])) if kernel_ms else None,
         "algorithmic_bytes_per_launch": algo_bytes, "scratch_bytes_per_launch": int(scratch_bytes),
     }
@@ -289,6 +295,29 @@ def run_gpu_arm(args):
            "api": "cpctools_b200.timeSOAPfromCompressed(pinned host tensor) -> host results"}
     del host
 
+    # single-window calls on the same tile (what one reference call timeSOAP(window=w) costs)
+    single = {}
+    for w in (1, 50):
+        for _ in range(2):
+            timelag_device(X, (w,), _lib.KIND_SIMPLE, 1, mult=mult)
+        torch.cuda.synchronize()
+        _lib.profile_enable(True)
+        for _ in range(3):
+            timelag_device(X, (w,), _lib.KIND_SIMPLE, 1, mult=mult)
+        torch.cuda.synchronize()
+        ms = float(np.median(_lib.profile_read(_lib.PROF_TIMELAG)))
+        _lib.profile_enable(False)
+        nb = frames * atoms * dc * 8 + (frames - w) * atoms * 8
+        single[f"window_{w}"] = {"kernel_ms": ms, "GBps": nb / ms / 1e6, "frac": nb / ms / 1e6 / peak,
+                                 "pairs_per_s": (frames - w) * atoms / ms * 1e3}
+    roofline["single_window_calls"] = single
+    del X, out
+    torch.cuda.empty_cache()
+
+    allpairs = None
+    if not args.no_allpairs:
+        allpairs = run_allpairs(args, torch, dist, _lib, rank, world)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         raw, sl = cpu_sample(args.ref_frames, args.ref_atoms)
@@ -312,12 +341,75 @@ def run_gpu_arm(args):
                        "pairs_per_step": pairs_step, "l2": "inputs (>= 100 GB per GPU) far larger than the 126 MB L2",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "allpairs": allpairs,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_allpairs(args, torch, dist, _lib, rank, world):
+    """BASELINE configs[3]: all-pairs SOAP distance matrix of 200 000 normalised vectors (D = 576),
+    row blocks of 25 000 rows per GPU (8 GPUs = the whole 4e10-pair matrix; fewer GPUs = that share of
+    it: weak scaling).  The vector set is generated on rank 0 and broadcast over NCCL; the distance
+    blocks stay on their GPU (320 GB in total), only a checksum is reduced."""
+    from cpctools_b200.classify import pairs_device
+    from cpctools_b200.sharding import shard_range
+
+    n_total, dim, parts = args.allpairs_vectors, 576, 8
+    out = {"vectors": n_total, "dim": dim, "rows_per_gpu": None, "metric": "SOAP vector-pairs/sec (all-pairs SOAPdistanceNormalized matrix)"}
+    bf16 = None
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        bf16 = float(json.load(open(path))["bf16_tflops"])
+    for dt, name, nd, kpad in ((torch.float64, "f64", 6, 576), (torch.float32, "f32", 3, 640)):
+        X = torch.empty((n_total, dim), dtype=dt, device="cuda")
+        if rank == 0:
+            _lib.check(_lib.load().soap_fill_uniform(X.data_ptr(), X.numel(), 777, _lib.F64 if dt == torch.float64 else _lib.F32, None), "fill")
+            X = torch.nn.functional.normalize(X, dim=-1)
+        if world > 1:
+            dist.broadcast(X, src=0)
+        rows = shard_range(n_total, rank % parts, parts)
+        block = torch.empty((rows.stop - rows.start, n_total), dtype=dt, device="cuda")
+        fn = lambda: pairs_device(X[rows], X, _lib.KIND_NORMALIZED, 1, path=_lib.PAIRS_TENSOR, out=block)
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        reps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.profile_enable(True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        kms = float(np.mean(_lib.profile_read(_lib.PROF_PAIRS)))
+        _lib.profile_enable(False)
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+        chk = block[:64, :4096].double().sum().reshape(1)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(chk)
+        pairs = (rows.stop - rows.start) * n_total * world
+        passes = nd * (nd + 1) // 2
+        int8_tops = passes * 2.0 * (rows.stop - rows.start) * n_total * kpad / (kms * 1e-3) / 1e12
+        out[name] = {
+            "value": pairs / (float(ms.item()) * 1e-3), "unit": "pairs/s", "ms_per_step": float(ms.item()),
+            "equiv_tflops": 2.0 * pairs * dim / (float(ms.item()) * 1e-3) / 1e12,
+            "kernel": f"pairs_i8_kernel<ND={nd}> (tcgen05.mma.kind::i8, {passes} exact digit passes)",
+            "roofline": {"bound": "tensor", "achieved": int8_tops, "unit": "TOP/s (int8, executed)",
+                         "peak": None if bf16 is None else 2.0 * bf16,
+                         "frac": None if bf16 is None else int8_tops / (2.0 * bf16),
+                         "peak_source": "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json); int8 dense = 2 x bf16 on sm_100",
+                         "kernel_ms": kms},
+            "checksum_sample": float(chk.item()),
+        }
+        out["rows_per_gpu"] = rows.stop - rows.start
+        del block, X
+        torch.cuda.empty_cache()
+    return out
 
 
 def ctypes_int_array(vals):
@@ -338,6 +430,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=1000)
     ap.add_argument("--ref-atoms", type=int, default=24, help="atoms of the bounded CPU sample per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-allpairs", action="store_true")
+    ap.add_argument("--allpairs-vectors", type=int, default=200000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
