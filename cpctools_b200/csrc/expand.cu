@@ -11,6 +11,8 @@
 // The int32 gather table lives in shared memory and is hoisted into registers per column chunk.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace soapb {
 
 template <typename T>
@@ -25,6 +27,7 @@ template <>
 struct VecOf<uint32_t> { static constexpr int N = 4; };
 
 constexpr int kExpandThreads = 256;
+constexpr int kMaxSplit = 4;  // warps that may share one vector in the norm phase
 
 template <typename T>
 __device__ __forceinline__ T scale_elem(T v, double nrm) {
@@ -38,6 +41,26 @@ __device__ __forceinline__ double scale_elem<double>(double v, double nrm) {
 template <>
 __device__ __forceinline__ float scale_elem<float>(float v, double nrm) {
   return v / (float)nrm;
+}
+
+template <typename T>
+__device__ __forceinline__ unsigned long long pun64(T v) {
+  static_assert(sizeof(T) == 8, "");
+  return *reinterpret_cast<unsigned long long *>(&v);
+}
+template <typename T>
+__device__ __forceinline__ unsigned int pun32(T v) {
+  static_assert(sizeof(T) == 4, "");
+  return *reinterpret_cast<unsigned int *>(&v);
+}
+
+template <typename T>
+__device__ __forceinline__ float to_float(T v) {
+  return 0.f;
+}
+template <>
+__device__ __forceinline__ float to_float<float>(float v) {
+  return v;
 }
 
 template <typename T>
@@ -66,11 +89,12 @@ __global__ void __launch_bounds__(kExpandThreads, 2)
 
   const size_t stage_elems = (size_t)tv * in_stride;
   const size_t stage_bytes = ((stage_elems * sizeof(T)) + 127) & ~(size_t)127;
-  T *stage[2] = {reinterpret_cast<T *>(smem_raw), reinterpret_cast<T *>(smem_raw + stage_bytes)};
+  auto stage = [&](int i) { return reinterpret_cast<T *>(smem_raw + (size_t)i * stage_bytes); };
   int32_t *tab = reinterpret_cast<int32_t *>(smem_raw + 2 * stage_bytes);
   const int d_pad = (d_full + 3) & ~3;
   double *nrm = reinterpret_cast<double *>(tab + (HAS_IDX ? d_pad : 0));
-  uint64_t *bar = reinterpret_cast<uint64_t *>(nrm + ((tv + 1) & ~1));
+  double *parts = nrm + ((tv + 1) & ~1);  // [tv][kMaxSplit] partial square sums
+  uint64_t *bar = reinterpret_cast<uint64_t *>(parts + (size_t)tv * kMaxSplit);
 
   const long long ntiles = (nvec + tv - 1) / tv;
   if (HAS_IDX) {
@@ -90,12 +114,12 @@ __global__ void __launch_bounds__(kExpandThreads, 2)
   auto issue = [&](long long t, int s) {  // thread 0 only, bulk path
     const uint32_t bytes = (uint32_t)((size_t)tile_rows(t) * in_stride * sizeof(T));
     mbar_expect_tx(&bar[s], bytes);
-    bulk_g2s(stage[s], in + (size_t)t * tv * in_stride, bytes, &bar[s]);
+    bulk_g2s(stage(s), in + (size_t)t * tv * in_stride, bytes, &bar[s]);
   };
 
   long long t = blockIdx.x;
   int s = 0;
-  uint32_t phase[2] = {0, 0};
+  uint32_t phase_bits = 0;  // bit s = parity of the next completion of bar[s]
   if (bulk_ok && tid == 0 && t < ntiles) issue(t, 0);
 
   for (; t < ntiles; t += gridDim.x, s ^= 1) {
@@ -104,51 +128,111 @@ __global__ void __launch_bounds__(kExpandThreads, 2)
       const long long tn = t + gridDim.x;
       // stage s^1 was last read in the previous iteration (trailing __syncthreads below)
       if (tid == 0 && tn < ntiles) issue(tn, s ^ 1);
-      mbar_wait(&bar[s], phase[s]);
-      phase[s] ^= 1;
+      mbar_wait(&bar[s], (phase_bits >> s) & 1u);
+      phase_bits ^= 1u << s;
     } else {
       const T *src = in + (size_t)t * tv * in_stride;
       const int n = rows * in_stride;
-      for (int i = tid; i < n; i += kExpandThreads) stage[s][i] = src[i];
+      for (int i = tid; i < n; i += kExpandThreads) stage(s)[i] = src[i];
       __syncthreads();
     }
-    const T *sm = stage[s];
+    const T *sm = stage(s);
 
     if (NORM) {
-      // phase 1: one warp per vector, squared norm of the EXPANDED vector in double
-      for (int v = warp; v < rows; v += kWarps) {
-        const T *row = sm + (size_t)v * in_stride;
+      // phase 1: squared norm of the EXPANDED vector.  Each vector is summed by `32/L * split`
+      // lane groups: half warps when the tile holds more vectors than warps (short rows), several
+      // warps per vector when it holds fewer (long rows); 4 independent chains per lane.
+      const int L = rows > kWarps ? 16 : 32;                       // lanes per group
+      const int slots = kWarps * (32 / L);                         // groups available per round
+      const int split = rows < slots ? (slots / rows < kMaxSplit ? slots / rows : kMaxSplit) : 1;
+      const int grp = warp * (32 / L) + lane / L, sl = lane % L;
+      for (int v0 = 0; v0 < rows; v0 += slots / split) {
+        const int v = v0 + grp / split, part = grp % split;
         double acc = 0.0;
-        for (int j = lane; j < d_full; j += 32) acc += sq_as_double<T>(row[HAS_IDX ? tab[j] : j]);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-          double r = sqrt(acc);
-          nrm[v] = (r == 0.0) ? 1.0 : r;
+        if (v < rows && grp / split < slots / split) {
+          const T *row = sm + (size_t)v * in_stride;
+          const int step = L * split;
+          int j = sl + part * L;
+          if constexpr (sizeof(T) == 4) {
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;  // fp32 partials over a slice of the row
+            for (; j + 3 * step < d_full; j += 4 * step) {
+              const float e0 = to_float(row[HAS_IDX ? tab[j] : j]), e1 = to_float(row[HAS_IDX ? tab[j + step] : j + step]);
+              const float e2 = to_float(row[HAS_IDX ? tab[j + 2 * step] : j + 2 * step]);
+              const float e3 = to_float(row[HAS_IDX ? tab[j + 3 * step] : j + 3 * step]);
+              p0 = fmaf(e0, e0, p0); p1 = fmaf(e1, e1, p1); p2 = fmaf(e2, e2, p2); p3 = fmaf(e3, e3, p3);
+            }
+            for (; j < d_full; j += step) {
+              const float e0 = to_float(row[HAS_IDX ? tab[j] : j]);
+              p0 = fmaf(e0, e0, p0);
+            }
+            acc = ((double)p0 + (double)p1) + ((double)p2 + (double)p3);
+          } else {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (; j + 3 * step < d_full; j += 4 * step) {
+              a0 += sq_as_double<T>(row[HAS_IDX ? tab[j] : j]);
+              a1 += sq_as_double<T>(row[HAS_IDX ? tab[j + step] : j + step]);
+              a2 += sq_as_double<T>(row[HAS_IDX ? tab[j + 2 * step] : j + 2 * step]);
+              a3 += sq_as_double<T>(row[HAS_IDX ? tab[j + 3 * step] : j + 3 * step]);
+            }
+            for (; j < d_full; j += step) a0 += sq_as_double<T>(row[HAS_IDX ? tab[j] : j]);
+            acc = (a0 + a1) + (a2 + a3);
+          }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double other = __shfl_xor_sync(0xffffffffu, acc, o);
+          if (o < L) acc += other;
+        }
+        if (v < rows && sl == 0 && grp / split < slots / split) parts[v * kMaxSplit + part] = acc;
+      }
+      __syncthreads();
+      if (tid < rows) {
+        double acc = 0.0;
+        for (int p = 0; p < split; ++p) acc += parts[tid * kMaxSplit + p];
+        const double r = sqrt(acc);
+        nrm[tid] = (r == 0.0) ? 1.0 : r;
       }
       __syncthreads();
     }
 
-    // phase 2: gather (+ scale) and stream out
+    // phase 2: gather (+ scale) and stream out.  A thread owns one 16-byte column chunk (gather
+    // indices hoisted into registers) and walks the tile's vectors; the chunks left over after the
+    // last full round of 256 are shared out by ROWS between thread groups, so short rows (e.g. 288
+    // chunks) keep every warp busy
     T *dst = out + (size_t)t * tv * d_full;
     if (vec_ok) {
       const int nchunk = d_full / V;  // d_full % V == 0 when vec_ok
-      for (int c = tid; c < nchunk; c += kExpandThreads) {
+      auto sweep = [&](int c, int v_first, auto step_tag, int v_step_rt) {
+        // full rounds walk every vector (compile-time stride 1, so the 4-way unroll really happens)
+        const int v_step = decltype(step_tag)::value ? 1 : v_step_rt;
         int col[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) col[k] = HAS_IDX ? tab[c * V + k] : (c * V + k);
 #pragma unroll 4
-        for (int v = 0; v < rows; ++v) {
+        for (int v = v_first; v < rows; v += v_step) {
           const T *row = sm + (size_t)v * in_stride;
-          union {
-            int4 q;
-            T e[V];
-          } u;
+          T e[V];
           const double nv = NORM ? nrm[v] : 1.0;
 #pragma unroll
-          for (int k = 0; k < V; ++k) u.e[k] = NORM ? scale_elem<T>(row[col[k]], nv) : row[col[k]];
-          stg_stream16(dst + (size_t)v * d_full + (size_t)c * V, u.q);
+          for (int k = 0; k < V; ++k) e[k] = NORM ? scale_elem<T>(row[col[k]], nv) : row[col[k]];
+          int4 q;
+          if constexpr (sizeof(T) == 8) {
+            q = make_int4((int)(pun64(e[0]) & 0xffffffffu), (int)(pun64(e[0]) >> 32), (int)(pun64(e[1]) & 0xffffffffu),
+                          (int)(pun64(e[1]) >> 32));
+          } else {
+            q = make_int4((int)pun32(e[0]), (int)pun32(e[1]), (int)pun32(e[2]), (int)pun32(e[3]));
+          }
+          stg_stream16(dst + (size_t)v * d_full + (size_t)c * V, q);
         }
+      };
+      const int full = (nchunk / kExpandThreads) * kExpandThreads;
+      for (int c = tid; c < full; c += kExpandThreads) sweep(c, 0, std::true_type{}, 1);
+      const int rem = nchunk - full;
+      if (rem > 0) {
+        const int rem_pad = (rem + 31) & ~31;
+        const int groups = kExpandThreads / rem_pad;  // >= 1
+        const int grp = tid / rem_pad, cl = tid - grp * rem_pad;
+        if (grp < groups && cl < rem) sweep(full + cl, grp, std::false_type{}, groups);
       }
     } else {
       const int total = rows * d_full;
@@ -174,7 +258,7 @@ static int launch_expand(const void *in, void *out, const int32_t *idx, int64_t 
   if ((int64_t)tv > nvec) tv = (int)nvec;
   const size_t stage_bytes = (((size_t)tv * row_bytes) + 127) & ~(size_t)127;
   const int d_pad = (d_full + 3) & ~3;
-  const size_t smem = 2 * stage_bytes + (idx ? (size_t)d_pad * 4 : 0) + ((tv + 1) & ~1) * 8 + 16;
+  const size_t smem = 2 * stage_bytes + (idx ? (size_t)d_pad * 4 : 0) + ((tv + 1) & ~1) * 8 + (size_t)tv * kMaxSplit * 8 + 16;
   if (smem > (size_t)max_smem_optin())
     return set_error(SOAP_EUNSUPPORTED, "soap_expand: a single vector of %zu bytes does not fit in shared memory",
                      row_bytes);
