@@ -8,7 +8,7 @@
 // round-toward-zero, a one-sided bias of ~0.5 ulp per slice; over K = 576 x 3 passes it reaches
 // 6e-6 on the kernel value (measured, pairs_tf32.cu), above the 1e-6 tolerance of the fp32 path.
 // Integer accumulation has no rounding at all:
-//   every row is scaled by sigma_i = max|x_i| / (126.5 * 2^(8(ND-1))) and rounded to an integer
+//   every row is scaled by the power of two sigma_i >= max|x_i| / (126.5 * 2^(8(ND-1))) and rounded to an integer
 //   X = sum_a d_a 2^(8(ND-1-a)) with ND balanced base-256 digits d_a in [-128,127] (int8 planes);
 //   x.y = sigma_i sigma_j sum_{a,b} 2^(8(2ND-2-a-b)) (d_a . d_b); the digit products d_a.d_b are
 //   int8 x int8 -> int32 tensor-core GEMMs, EXACT (|sum| <= 6 x 576 x 2^14 << 2^31); pairs with
@@ -22,6 +22,8 @@
 // (M128 x BN x K32 per instruction, ND(ND+1)/2 passes per K step into ND TMEM accumulators),
 // warps 2..9 drain TMEM (tcgen05.ld), recombine the digit sums, apply the distance and store.
 #include "tc05.cuh"
+
+#include <stdlib.h>
 
 namespace soapb {
 
@@ -60,7 +62,12 @@ __global__ void __launch_bounds__(256)
   acc = warp_sum(acc);
   const double cap = 126.5 * (double)(1ull << (8 * (ND - 1)));
   const bool finite = (acc == acc) && (acc < 1.0e308);
-  const double sigma = (mx > 0.0 && finite) ? mx / cap : 1.0;
+  // power-of-two scale >= max|x| / cap: scaling and un-scaling are then exact in every precision
+  int sexp = 0;
+  if (mx > 0.0 && finite) {
+    frexp(mx / cap, &sexp);  // mx/cap = m * 2^sexp, m in [0.5, 1)
+  }
+  const double sigma = ldexp(1.0, sexp);
   const double inv = 1.0 / sigma;
   if (lane == 0) {
     scale[row] = finite ? sigma * (double)(1ull << (8 * (ND - 1))) : __longlong_as_double(0x7ff8000000000000ll);
@@ -102,27 +109,27 @@ __device__ __forceinline__ void tile_coords_i8(long long t, int tiles_m, int til
   tn = first + (int)(r % width);
 }
 
-template <int ND, int BN, int BKB, typename OutT>
+template <int ND, int BN, int BKB, int ACC, typename OutT>
 __global__ void __launch_bounds__(kI8Threads, 1)
     pairs_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     OutT *__restrict__ out, const double *__restrict__ sa, const double *__restrict__ sb,
                     const double *__restrict__ uu, const double *__restrict__ vv, long long M, long long N, int KB,
-                    long long ldo, int kind, int power, int tiles_m, int tiles_n) {
+                    long long ldo, int kind, int power, int tiles_m, int tiles_n, int debug_flags) {
   constexpr int BM = kI8BM, STAGES = kI8Stages;
   constexpr int A_PLANE = BM * BKB, B_PLANE = BN * BKB;
   constexpr int STAGE_BYTES = ND * (A_PLANE + B_PLANE);
   constexpr int KS = BKB / 32;  // UMMA K = 32 for 8-bit operands
   // instruction descriptor: D = s32, A = B = signed int8, K-major, N = BN, M = 128
   constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-  static_assert(ND * BN <= 512, "accumulators exceed TMEM");
+  static_assert(ACC * ND * BN <= 512, "accumulators exceed TMEM");  // ACC = accumulator sets (2: epilogue overlaps the next tile)
   static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
   uint64_t *full = bars, *empty = bars + STAGES;
-  uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = tmem_full + 1;
-  uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+  uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = tmem_full + ACC;
+  uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tiles = (long long)tiles_m * tiles_n;
@@ -132,8 +139,10 @@ __global__ void __launch_bounds__(kI8Threads, 1)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, kI8EpiWarps);
+    for (int a = 0; a < ACC; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kI8EpiWarps);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -173,8 +182,10 @@ __global__ void __launch_bounds__(kI8Threads, 1)
     uint32_t ph = 0;
     int it = 0;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-      mbar_wait_guard(tmem_empty, (uint32_t)((it & 1) ^ 1));  // epilogue has drained the previous tile
+      const int as = it % ACC;
+      mbar_wait_guard(&tmem_empty[as], (uint32_t)(((it / ACC) & 1) ^ 1));  // epilogue has drained this accumulator set
       tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(as * ND * BN);
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait_guard(&full[s], ph);
         tc_fence_after();
@@ -192,12 +203,13 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                 const uint32_t pb = st + ND * A_PLANE + b * B_PLANE;
                 const uint64_t db = (BKB == 128 ? umma_desc_sw128(pb) : umma_desc_sw64(pb)) + adv;
                 // digit pairs of equal weight a+b share accumulator g = a+b; (0, g) is its first pass
-                tc_mma_i8(tmem_base + (uint32_t)((a + b) * BN), da, db, IDESC, (kb | ks | a) != 0 ? 1u : 0u);
+                if (!(debug_flags & 2) || (a | b | ks) == 0)
+                  tc_mma_i8(tmem_acc + (uint32_t)((a + b) * BN), da, db, IDESC, (kb | ks | a) != 0 ? 1u : 0u);
               }
             }
           }
           tc_commit(&empty[s]);
-          if (kb == KB - 1) tc_commit(tmem_full);
+          if (kb == KB - 1) tc_commit(&tmem_full[as]);
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -215,50 +227,79 @@ __global__ void __launch_bounds__(kI8Threads, 1)
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       int tm, tn;
       tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
-      mbar_wait_guard(tmem_full, (uint32_t)(it & 1));
+      const int as = it % ACC;
+      mbar_wait_guard(&tmem_full[as], (uint32_t)((it / ACC) & 1));
       tc_fence_after();
       const long long row = (long long)tm * BM + q * 32 + lane;
       const bool row_ok = row < M;
       const double si = row_ok ? sa[row] : 0.0;
+      const int ei = (__double2hiint(si) >> 20) & 0x7ff;  // biased exponent of the (power-of-two) row scale
       const double ui = (need_norms && row_ok) ? uu[row] : 1.0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(as * ND * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = part; c < BN / 16; c += PARTS) {
+      for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 16); c += PARTS) {
         uint32_t v[ND][16];
 #pragma unroll
         for (int g = 0; g < ND; ++g) tmem_ld16(taddr + (uint32_t)(g * BN + c * 16), v[g]);
-        tmem_ld_wait();
         const long long col0 = (long long)tn * BN + c * 16;
+        const bool full_chunk = col0 + 16 <= N;
+        // column scales of this chunk (same 128 bytes for every lane: broadcast loads, L1 resident)
+        double sbj[16];
+        if (full_chunk) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const double2 two = *reinterpret_cast<const double2 *>(sb + col0 + j);  // col0 is a multiple of 16
+            sbj[j] = two.x;
+            sbj[j + 1] = two.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sbj[j] = (col0 + j < N) ? sb[col0 + j] : 0.0;
+        }
+        tmem_ld_wait();
         if (row_ok && col0 < N) {
           OutT r[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const long long col = col0 + j;
             const bool col_ok = col < N;
+            // x.y = scale_i scale_j sum_g S_g 2^(-8g): the digit sums are exact integers, the scales
+            // exact powers of two
             double tsum;
-            if constexpr (ND <= 3) {
-              long long acc = 0;  // exact: |acc| < 2^45
-#pragma unroll
-              for (int g = 0; g < ND; ++g) acc = acc * 256 + (long long)(int)v[g][j];
-              tsum = (double)acc * (1.0 / (double)(1ull << (8 * (ND - 1))));
-            } else {
-              tsum = (double)(int)v[ND - 1][j];
-#pragma unroll
-              for (int g = ND - 2; g >= 0; --g) tsum = fma(tsum, 1.0 / 256.0, (double)(int)v[g][j]);
-            }
-            const double gdot = si * (col_ok ? sb[col] : 0.0) * tsum;
-            if constexpr (sizeof(OutT) == 4) {
-              if (!need_norms) {
-                r[j] = sqrtf(fabsf(2.0f - 2.0f * (float)gdot));  // SOAPdistanceNormalized in float32
-              } else {
-                r[j] = (OutT)soap_epilogue(gdot, ui, col_ok ? vv[col] : 1.0, kind, power);
+            if constexpr (ND == 3) {
+              // |S0| < 2^24 is exact in fp32; the two lower digit sums only need ~16 and ~8 bits
+              const float tf = fmaf(fmaf((float)(int)v[2][j], 1.0f / 256.0f, (float)(int)v[1][j]), 1.0f / 256.0f,
+                                    (float)(int)v[0][j]);
+              if (sizeof(OutT) == 4 && !need_norms) {
+                // SOAPdistanceNormalized, float32 result (distances.py:83), all in fp32: tf carries ONE
+                // rounding, the scaling is exact, 2-2g is exact for g in [1/2, 2] (Sterbenz), the
+                // square root is the 1-ulp hardware approximation
+                const int ej = (__double2hiint(sbj[j]) >> 20) & 0x7ff;
+                int k = ei + ej - 2 * 1023;
+                k = k < -126 ? -126 : (k > 127 ? 127 : k);
+                const float pw = (ei == 0x7ff || ej == 0x7ff) ? __int_as_float(0x7fc00000) : __int_as_float((k + 127) << 23);
+                float rt;
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(rt) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
+                r[j] = (OutT)rt;
+                continue;
               }
+              tsum = (double)tf;
             } else {
-              r[j] = (OutT)soap_epilogue(gdot, ui, (need_norms && col_ok) ? vv[col] : 1.0, kind, power);
+              // ND == 6: two exact 64-bit integers (three digit sums each), two conversions
+              long long hi = 0, lo = 0;
+#pragma unroll
+              for (int g = 0; g < ND / 2; ++g) hi = hi * 256 + (long long)(int)v[g][j];
+#pragma unroll
+              for (int g = ND / 2; g < ND; ++g) lo = lo * 256 + (long long)(int)v[g][j];
+              constexpr double kHi = 1.0 / (double)(1ull << (8 * (ND / 2 - 1)));
+              constexpr double kLo = 1.0 / (double)(1ull << (8 * (ND - 1)));
+              tsum = fma((double)lo, kLo, (double)hi * kHi);
             }
+            const double gdot = (si * sbj[j]) * tsum;
+            r[j] = (OutT)soap_epilogue(gdot, ui, (need_norms && col_ok) ? vv[col] : 1.0, kind, power);
           }
           OutT *dst = out + (size_t)row * ldo + col0;
-          if (vec_ok && col0 + 16 <= N) {
+          if (vec_ok && full_chunk) {
 #pragma unroll
             for (int j = 0; j < 16; j += VEC) *reinterpret_cast<int4 *>(dst + j) = *reinterpret_cast<const int4 *>(&r[j]);
           } else {
@@ -270,7 +311,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty);
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
   }
 
@@ -289,7 +330,7 @@ static size_t i8_scratch_bytes(int64_t M, int64_t N, int D) {
   return align_up((size_t)ND * M * Dp, 1024) + align_up((size_t)ND * N * Dp, 1024) + (size_t)(M + N) * 16 + 4096;
 }
 
-template <typename InT, int ND, int BN, int BKB, typename OutT>
+template <typename InT, int ND, int BN, int BKB, int ACC, typename OutT>
 static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                            int power, void *scratch, cudaStream_t s) {
   SOAP_REQUIRE(out != nullptr, "soap_pairs: the tensor-core path writes the full matrix (out == NULL)");
@@ -323,11 +364,18 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   const long long tiles = (long long)tiles_m * tiles_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   constexpr size_t SMEM = 1024 + (size_t)kI8Stages * ND * (kI8BM + BN) * BKB + 256;
-  auto kern = pairs_i8_kernel<ND, BN, BKB, OutT>;
+  auto kern = pairs_i8_kernel<ND, BN, BKB, ACC, OutT>;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   ProfScope prof(SOAP_PROF_PAIRS, s);
-  kern<<<grid, kI8Threads, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n);
+  const char *dbg = getenv("SOAP_I8_DEBUG");  // experiments: 1 = skip the epilogue, 2 = one MMA per K block
+  kern<<<grid, kI8Threads, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n,
+                                      dbg ? atoi(dbg) : 0);
   return check_launch("pairs_i8_kernel");
+}
+
+static int env_variant() {
+  const char *v = getenv("SOAP_I8_VARIANT");  // 1 = single accumulator set with wide tiles (experiments)
+  return v ? atoi(v) : 0;
 }
 
 size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
@@ -336,12 +384,14 @@ size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
 
 int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
-  return launch_pairs_i8<float, 3, 160, 128, float>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
+  if (env_variant() == 1) return launch_pairs_i8<float, 3, 160, 128, 1, float>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
+  return launch_pairs_i8<float, 3, 80, 128, 2, float>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
 }
 
 int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
-  return launch_pairs_i8<double, 6, 80, 64, double>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
+  if (env_variant() == 1) return launch_pairs_i8<double, 6, 80, 64, 1, double>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
+  return launch_pairs_i8<double, 6, 32, 64, 2, double>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
 }
 
 }  // namespace soapb
