@@ -230,6 +230,15 @@ def _expand(x, plan: ExpansionPlan, normalize: bool, who: str):
         raise ValueError(f"{who}: the given soap vector do not have the expected dimensions")
     th = _device.require_cuda()
     lib = _lib.load()
+    restore = None  # numpy dtypes the gather kernel does not move natively (1- and 2-byte elements)
+    if not normalize and not _device.is_tensor(x):
+        arr = np.asarray(x)
+        if arr.dtype.kind == "u" and arr.dtype.itemsize in (4, 8):
+            restore = ("view", arr.dtype)  # a gather moves bits: reinterpret as the signed type
+            x = np.ascontiguousarray(arr).view(np.int32 if arr.dtype.itemsize == 4 else np.int64)
+        elif arr.dtype.itemsize not in (4, 8) or arr.dtype.kind not in "fi":
+            restore = ("cast", arr.dtype)
+            x = arr.astype(np.float32 if arr.dtype.kind == "f" else np.int64)
     src = _device.as_float_tensor(x) if normalize else _device.to_device(x)
     if src.dtype == th.bool or src.element_size() not in (4, 8):
         src = src.to(th.int64 if not src.dtype.is_floating_point else th.float32)
@@ -247,7 +256,10 @@ def _expand(x, plan: ExpansionPlan, normalize: bool, who: str):
             src.element_size(), _device.stream_ptr(),
         )
     _lib.check(rc, who)
-    return _device.like_input(out, x)
+    res = _device.like_input(out, x)
+    if restore is None:
+        return res
+    return res.view(restore[1]) if restore[0] == "view" else res.astype(restore[1])
 
 
 def fillSOAPVectorFromdscribe(soapFromdscribe, lMax: int, nMax: int, atomTypes: list = None, atomicSlices: dict = None):

@@ -96,6 +96,23 @@ def test_fill_large_tiles_and_ragged_tail(S):
     assert S.fillSOAPVectorFromdscribe(empty, 8, 8, ["H", "O"], sl).shape == (0, 1728)
 
 
+def test_fill_small_dtypes_and_tiny_shapes(S):
+    """element sizes the gather kernel does not move natively keep their dtype; degenerate shapes."""
+    rng = np.random.default_rng(2)
+    for dt in (np.int16, np.uint8, np.float16, np.uint32):
+        a = rng.integers(0, 100, size=(3, 324)).astype(dt)
+        got = S.fillSOAPVectorFromdscribe(a, 8, 8)
+        assert got.dtype == dt
+        assert_array_equal(got, O.fillSOAPVectorFromdscribe(a, 8, 8))
+    one = rng.random((1, 1, 1))  # nMax = 1, lMax = 0: a single slot
+    assert_array_equal(S.fillSOAPVectorFromdscribe(one, 0, 1), one)
+    X = O.normalizeArray(rng.random((2, 1, 3)))
+    t, dt_ = S.timeSOAP(X, window=1)
+    assert t.shape == (1, 1) and dt_.shape == (1, 0)
+    assert_distance_parity(t, O.timeSOAP(X, window=1, returnDiff=False), "f64")
+    assert S.normalizeArray(np.zeros((0, 5))).shape == (0, 5)
+
+
 def test_fill_device_tensor_stays_on_device(S):
     import torch
 
