@@ -30,7 +30,6 @@ namespace soapb {
 constexpr int kI8BM = 128;
 constexpr int kI8EpiWarps = 8;                       // two per TMEM lane quarter: latency hiding in the epilogue
 constexpr int kI8Threads = 64 + 32 * kI8EpiWarps;
-constexpr int kI8Stages = 2;
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -109,13 +108,13 @@ __device__ __forceinline__ void tile_coords_i8(long long t, int tiles_m, int til
   tn = first + (int)(r % width);
 }
 
-template <int ND, int BN, int BKB, int ACC, typename OutT>
+template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, typename OutT>
 __global__ void __launch_bounds__(kI8Threads, 1)
     pairs_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     OutT *__restrict__ out, const double *__restrict__ sa, const double *__restrict__ sb,
                     const double *__restrict__ uu, const double *__restrict__ vv, long long M, long long N, int KB,
                     long long ldo, int kind, int power, int tiles_m, int tiles_n, int debug_flags) {
-  constexpr int BM = kI8BM, STAGES = kI8Stages;
+  constexpr int BM = kI8BM;
   constexpr int A_PLANE = BM * BKB, B_PLANE = BN * BKB;
   constexpr int STAGE_BYTES = ND * (A_PLANE + B_PLANE);
   constexpr int KS = BKB / 32;  // UMMA K = 32 for 8-bit operands
@@ -130,6 +129,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
   uint64_t *full = bars, *empty = bars + STAGES;
   uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = tmem_full + ACC;
   uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + ACC);
+  int *col_exp = reinterpret_cast<int *>(smem + (size_t)STAGES * STAGE_BYTES + 256);  // [kI8EpiWarps][BN] (FAST path)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tiles = (long long)tiles_m * tiles_n;
@@ -197,11 +197,11 @@ __global__ void __launch_bounds__(kI8Threads, 1)
 #pragma unroll
             for (int a = 0; a < ND; ++a) {
               const uint32_t pa = st + a * A_PLANE;
-              const uint64_t da = (BKB == 128 ? umma_desc_sw128(pa) : umma_desc_sw64(pa)) + adv;
+              const uint64_t da = (BKB == 128 ? umma_desc_sw128(pa) : BKB == 64 ? umma_desc_sw64(pa) : umma_desc_sw32(pa)) + adv;
 #pragma unroll
               for (int b = 0; b < ND - a; ++b) {
                 const uint32_t pb = st + ND * A_PLANE + b * B_PLANE;
-                const uint64_t db = (BKB == 128 ? umma_desc_sw128(pb) : umma_desc_sw64(pb)) + adv;
+                const uint64_t db = (BKB == 128 ? umma_desc_sw128(pb) : BKB == 64 ? umma_desc_sw64(pb) : umma_desc_sw32(pb)) + adv;
                 // digit pairs of equal weight a+b share accumulator g = a+b; (0, g) is its first pass
                 if (!(debug_flags & 2) || (a | b | ks) == 0)
                   tc_mma_i8(tmem_acc + (uint32_t)((a + b) * BN), da, db, IDESC, (kb | ks | a) != 0 ? 1u : 0u);
@@ -228,6 +228,67 @@ __global__ void __launch_bounds__(kI8Threads, 1)
       int tm, tn;
       tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
       const int as = it % ACC;
+      if constexpr (FAST) {
+        // fp32 SOAPdistanceNormalized (distances.py:83) entirely in fp32: the scales are powers of two
+        // (exact), tf carries ONE rounding, 2-2g is exact for g in [1/2, 2] (Sterbenz), the square root
+        // is the 1-ulp hardware approximation.  Global reads (row / column scale exponents) are issued
+        // before the accumulator wait; column exponents sit in a per-warp shared array.
+        const long long row = (long long)tm * BM + q * 32 + lane;
+        const bool row_ok = row < M;
+        const int ei = row_ok ? ((__double2hiint(sa[row]) >> 20) & 0x7ff) : 0x7ff;
+        int *my_exp = col_exp + (warp - 2) * BN;
+        for (int cidx = lane; cidx < BN; cidx += 32) {
+          const long long col = (long long)tn * BN + cidx;
+          my_exp[cidx] = col < N ? ((__double2hiint(sb[col]) >> 20) & 0x7ff) : 0x7ff;
+        }
+        __syncwarp();
+        mbar_wait_guard(&tmem_full[as], (uint32_t)((it / ACC) & 1));
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(as * ND * BN) + ((uint32_t)(q * 32) << 16);
+        const bool vec4 = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll 1
+        for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 16); c += PARTS) {
+          uint32_t v[ND][16];
+#pragma unroll
+          for (int g = 0; g < ND; ++g) tmem_ld16(taddr + (uint32_t)(g * BN + c * 16), v[g]);
+          int ej[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const int4 e4 = *reinterpret_cast<const int4 *>(my_exp + c * 16 + j);
+            ej[j] = e4.x; ej[j + 1] = e4.y; ej[j + 2] = e4.z; ej[j + 3] = e4.w;
+          }
+          tmem_ld_wait();
+          const long long col0 = (long long)tn * BN + c * 16;
+          float *dst = reinterpret_cast<float *>(out) + (size_t)row * ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const int jj = j + k4;
+              const float tf = fmaf(fmaf((float)(int)v[2][jj], 1.0f / 256.0f, (float)(int)v[1][jj]), 1.0f / 256.0f,
+                                    (float)(int)v[0][jj]);
+              int k = ei + ej[jj] - 2 * 1023;
+              k = k < -126 ? -126 : (k > 127 ? 127 : k);
+              const float pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __int_as_float(0x7fc00000) : __int_as_float((k + 127) << 23);
+              asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
+            }
+            if (row_ok) {
+              if (vec4 && col0 + j + 4 <= N) {
+                *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                  if (col0 + j + k4 < N) dst[j + k4] = o[k4];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        continue;
+      }
       mbar_wait_guard(&tmem_full[as], (uint32_t)((it / ACC) & 1));
       tc_fence_after();
       const long long row = (long long)tm * BM + q * 32 + lane;
@@ -270,19 +331,6 @@ __global__ void __launch_bounds__(kI8Threads, 1)
               // |S0| < 2^24 is exact in fp32; the two lower digit sums only need ~16 and ~8 bits
               const float tf = fmaf(fmaf((float)(int)v[2][j], 1.0f / 256.0f, (float)(int)v[1][j]), 1.0f / 256.0f,
                                     (float)(int)v[0][j]);
-              if (sizeof(OutT) == 4 && !need_norms) {
-                // SOAPdistanceNormalized, float32 result (distances.py:83), all in fp32: tf carries ONE
-                // rounding, the scaling is exact, 2-2g is exact for g in [1/2, 2] (Sterbenz), the
-                // square root is the 1-ulp hardware approximation
-                const int ej = (__double2hiint(sbj[j]) >> 20) & 0x7ff;
-                int k = ei + ej - 2 * 1023;
-                k = k < -126 ? -126 : (k > 127 ? 127 : k);
-                const float pw = (ei == 0x7ff || ej == 0x7ff) ? __int_as_float(0x7fc00000) : __int_as_float((k + 127) << 23);
-                float rt;
-                asm("sqrt.approx.f32 %0, %1;" : "=f"(rt) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
-                r[j] = (OutT)rt;
-                continue;
-              }
               tsum = (double)tf;
             } else {
               // ND == 6: two exact 64-bit integers (three digit sums each), two conversions
@@ -330,7 +378,7 @@ static size_t i8_scratch_bytes(int64_t M, int64_t N, int D) {
   return align_up((size_t)ND * M * Dp, 1024) + align_up((size_t)ND * N * Dp, 1024) + (size_t)(M + N) * 16 + 4096;
 }
 
-template <typename InT, int ND, int BN, int BKB, int ACC, typename OutT>
+template <typename InT, int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, typename OutT>
 static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                            int power, void *scratch, cudaStream_t s) {
   SOAP_REQUIRE(out != nullptr, "soap_pairs: the tensor-core path writes the full matrix (out == NULL)");
@@ -356,15 +404,15 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
     ozaki_split_kernel<InT, ND><<<(unsigned)((N + 7) / 8), 256, 0, s>>>(B, pb, sb, ub, N, D, Dp);
     if ((rc = check_launch("ozaki_split_kernel"))) return rc;
   }
-  const CUtensorMapSwizzle swz = BKB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle swz = BKB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : BKB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap map_a, map_b;
   if ((rc = make_tensor_map_2d(&map_a, pa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * M, Dp, BKB, kI8BM, swz))) return rc;
   if ((rc = make_tensor_map_2d(&map_b, pb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * N, Dp, BKB, BN, swz))) return rc;
   const int tiles_m = (int)((M + kI8BM - 1) / kI8BM), tiles_n = (int)((N + BN - 1) / BN);
   const long long tiles = (long long)tiles_m * tiles_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  constexpr size_t SMEM = 1024 + (size_t)kI8Stages * ND * (kI8BM + BN) * BKB + 256;
-  auto kern = pairs_i8_kernel<ND, BN, BKB, ACC, OutT>;
+  constexpr size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)kI8EpiWarps * BN * 4;
+  auto kern = pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, OutT>;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   ProfScope prof(SOAP_PROF_PAIRS, s);
   const char *dbg = getenv("SOAP_I8_DEBUG");  // experiments: 1 = skip the epilogue, 2 = one MMA per K block
@@ -379,19 +427,37 @@ static int env_variant() {
 }
 
 size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
-  return dtype == SOAP_F64 ? i8_scratch_bytes<6, 64>(M, N, D) : i8_scratch_bytes<3, 128>(M, N, D);
+  // planes are padded to a multiple of 128 columns: valid for every K-block width used below
+  return dtype == SOAP_F64 ? i8_scratch_bytes<6, 128>(M, N, D) : i8_scratch_bytes<3, 128>(M, N, D);
 }
+
+#define I8_LAUNCH(IN, ND, BN, BKB, ACC, ST, FAST, OUT) \
+  launch_pairs_i8<IN, ND, BN, BKB, ACC, ST, FAST, OUT>(A, B, out, M, N, D, ldo, kind, power, scratch, s)
 
 int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
-  if (env_variant() == 1) return launch_pairs_i8<float, 3, 160, 128, 1, float>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
-  return launch_pairs_i8<float, 3, 80, 128, 2, float>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
+  if (kind == SOAP_KIND_NORMALIZED) {
+    // measured on 25 000^2 x 576 (ms): N160/K64/4 stages 2.19 | N80/K64/4 stages, 2 acc. sets 2.33 |
+    // N160/K128/2 stages 2.35 | N80/K128/2 stages, 2 acc. sets 2.41
+    switch (env_variant()) {
+      case 1: return I8_LAUNCH(float, 3, 160, 128, 1, 2, true, float);
+      case 2: return I8_LAUNCH(float, 3, 80, 64, 2, 4, true, float);
+      case 3: return I8_LAUNCH(float, 3, 80, 128, 2, 2, true, float);
+      default: return I8_LAUNCH(float, 3, 160, 64, 1, 4, true, float);
+    }
+  }
+  return I8_LAUNCH(float, 3, 80, 128, 2, 2, false, float);
 }
 
 int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
-  if (env_variant() == 1) return launch_pairs_i8<double, 6, 80, 64, 1, double>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
-  return launch_pairs_i8<double, 6, 32, 64, 2, double>(A, B, out, M, N, D, ldo, kind, power, scratch, s);
+  switch (env_variant()) {
+    case 1: return I8_LAUNCH(double, 6, 32, 64, 2, 2, false, double);
+    case 2: return I8_LAUNCH(double, 6, 80, 32, 1, 4, false, double);
+    case 3: return I8_LAUNCH(double, 6, 64, 32, 1, 4, false, double);
+    default: return I8_LAUNCH(double, 6, 80, 64, 1, 2, false, double);
+  }
 }
+#undef I8_LAUNCH
 
 }  // namespace soapb
