@@ -363,7 +363,7 @@ def run_allpairs(args, torch, dist, _lib, rank, world):
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         bf16 = float(json.load(open(path))["bf16_tflops"])
-    for dt, name, nd, kpad in ((torch.float64, "f64", 6, 576), (torch.float32, "f32", 3, 640)):
+    for dt, name, nd, kpad in ((torch.float64, "f64", 6, 576), (torch.float32, "f32", 3, 576)):  # K blocks of 64: 576 needs no padding
         X = torch.empty((n_total, dim), dtype=dt, device="cuda")
         if rank == 0:
             _lib.check(_lib.load().soap_fill_uniform(X.data_ptr(), X.numel(), 777, _lib.F64 if dt == torch.float64 else _lib.F32, None), "fill")
