@@ -38,6 +38,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- pre-pass: row scale, digit planes (zero padded to Dp), squared row norms ----------------------
@@ -229,10 +234,11 @@ __global__ void __launch_bounds__(kI8Threads, 1)
       tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
       const int as = it % ACC;
       if constexpr (FAST) {
-        // fp32 SOAPdistanceNormalized (distances.py:83) entirely in fp32: the scales are powers of two
-        // (exact), tf carries ONE rounding, 2-2g is exact for g in [1/2, 2] (Sterbenz), the square root
-        // is the 1-ulp hardware approximation.  Global reads (row / column scale exponents) are issued
-        // before the accumulator wait; column exponents sit in a per-warp shared array.
+        // SOAPdistanceNormalized (distances.py:83) with a lean, kind-specific epilogue.  fp32: entirely in
+        // fp32 -- the scales are powers of two (exact), tf carries ONE rounding, 2-2g is exact for g in
+        // [1/2, 2] (Sterbenz), the square root is the 1-ulp hardware approximation.  Global reads (row /
+        // column scale exponents) are issued before the accumulator wait; column exponents sit in a
+        // per-warp shared array.
         const long long row = (long long)tm * BM + q * 32 + lane;
         const bool row_ok = row < M;
         const int ei = row_ok ? ((__double2hiint(sa[row]) >> 20) & 0x7ff) : 0x7ff;
@@ -245,41 +251,92 @@ __global__ void __launch_bounds__(kI8Threads, 1)
         mbar_wait_guard(&tmem_full[as], (uint32_t)((it / ACC) & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(as * ND * BN) + ((uint32_t)(q * 32) << 16);
-        const bool vec4 = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        if constexpr (ND == 3) {
+          const bool vec4 = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 #pragma unroll 1
-        for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 16); c += PARTS) {
-          uint32_t v[ND][16];
+          for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 16); c += PARTS) {
+            uint32_t v[ND][16];
 #pragma unroll
-          for (int g = 0; g < ND; ++g) tmem_ld16(taddr + (uint32_t)(g * BN + c * 16), v[g]);
-          int ej[16];
+            for (int g = 0; g < ND; ++g) tmem_ld16(taddr + (uint32_t)(g * BN + c * 16), v[g]);
+            int ej[16];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const int4 e4 = *reinterpret_cast<const int4 *>(my_exp + c * 16 + j);
-            ej[j] = e4.x; ej[j + 1] = e4.y; ej[j + 2] = e4.z; ej[j + 3] = e4.w;
-          }
-          tmem_ld_wait();
-          const long long col0 = (long long)tn * BN + c * 16;
-          float *dst = reinterpret_cast<float *>(out) + (size_t)row * ldo + col0;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float o[4];
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const int jj = j + k4;
-              const float tf = fmaf(fmaf((float)(int)v[2][jj], 1.0f / 256.0f, (float)(int)v[1][jj]), 1.0f / 256.0f,
-                                    (float)(int)v[0][jj]);
-              int k = ei + ej[jj] - 2 * 1023;
-              k = k < -126 ? -126 : (k > 127 ? 127 : k);
-              const float pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __int_as_float(0x7fc00000) : __int_as_float((k + 127) << 23);
-              asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
+            for (int j = 0; j < 16; j += 4) {
+              const int4 e4 = *reinterpret_cast<const int4 *>(my_exp + c * 16 + j);
+              ej[j] = e4.x; ej[j + 1] = e4.y; ej[j + 2] = e4.z; ej[j + 3] = e4.w;
             }
-            if (row_ok) {
-              if (vec4 && col0 + j + 4 <= N) {
-                *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
-              } else {
+            tmem_ld_wait();
+            const long long col0 = (long long)tn * BN + c * 16;
+            float *dst = reinterpret_cast<float *>(out) + (size_t)row * ldo + col0;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                  if (col0 + j + k4 < N) dst[j + k4] = o[k4];
+            for (int j = 0; j < 16; j += 4) {
+              float o[4];
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const int jj = j + k4;
+                const float tf = fmaf(fmaf((float)(int)v[2][jj], 1.0f / 256.0f, (float)(int)v[1][jj]), 1.0f / 256.0f,
+                                      (float)(int)v[0][jj]);
+                int k = ei + ej[jj] - 2 * 1023;
+                k = k < -126 ? -126 : (k > 127 ? 127 : k);
+                const float pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __int_as_float(0x7fc00000) : __int_as_float((k + 127) << 23);
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
+              }
+              if (row_ok) {
+                if (vec4 && col0 + j + 4 <= N) {
+                  *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    if (col0 + j + k4 < N) dst[j + k4] = o[k4];
+                }
+              }
+            }
+          }
+        } else {
+          // fp64 SOAPdistanceNormalized: the six digit sums are folded into two exact 64-bit integers,
+          // converted once each; the power-of-two scaling is one exact multiply; IEEE sqrt
+          const bool vec2 = ((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+          constexpr double kHi = 1.0 / (double)(1ull << (8 * (ND / 2 - 1)));
+          constexpr double kLo = 1.0 / (double)(1ull << (8 * (ND - 1)));
+#pragma unroll 1
+          for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 8); c += PARTS) {
+            uint32_t v[ND][8];
+#pragma unroll
+            for (int g = 0; g < ND; ++g) tmem_ld8(taddr + (uint32_t)(g * BN + c * 8), v[g]);
+            int ej[8];
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const int4 e4 = *reinterpret_cast<const int4 *>(my_exp + c * 8 + j);
+              ej[j] = e4.x; ej[j + 1] = e4.y; ej[j + 2] = e4.z; ej[j + 3] = e4.w;
+            }
+            tmem_ld_wait();
+            const long long col0 = (long long)tn * BN + c * 8;
+            double *dst = reinterpret_cast<double *>(out) + (size_t)row * ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              double o[2];
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int jj = j + k2;
+                long long hi = 0, lo = 0;
+#pragma unroll
+                for (int g = 0; g < ND / 2; ++g) hi = hi * 256 + (long long)(int)v[g][jj];
+#pragma unroll
+                for (int g = ND / 2; g < ND; ++g) lo = lo * 256 + (long long)(int)v[g][jj];
+                const double tsum = fma((double)lo, kLo, (double)hi * kHi);
+                int k = ei + ej[jj] - 2 * 1023;
+                k = k < -1022 ? -1022 : (k > 1023 ? 1023 : k);
+                const double pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __longlong_as_double(0x7ff8000000000000ll)
+                                                                   : __hiloint2double((k + 1023) << 20, 0);
+                o[k2] = sqrt(fabs(fma(-2.0, tsum * pw, 2.0)));
+              }
+              if (row_ok) {
+                if (vec2 && col0 + j + 2 <= N) {
+                  *reinterpret_cast<double2 *>(dst + j) = make_double2(o[0], o[1]);
+                } else {
+#pragma unroll
+                  for (int k2 = 0; k2 < 2; ++k2)
+                    if (col0 + j + k2 < N) dst[j + k2] = o[k2];
+                }
               }
             }
           }
@@ -451,12 +508,15 @@ int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t 
 
 int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
-  switch (env_variant()) {
-    case 1: return I8_LAUNCH(double, 6, 32, 64, 2, 2, false, double);
-    case 2: return I8_LAUNCH(double, 6, 80, 32, 1, 4, false, double);
-    case 3: return I8_LAUNCH(double, 6, 64, 32, 1, 4, false, double);
-    default: return I8_LAUNCH(double, 6, 80, 64, 1, 2, false, double);
+  if (kind == SOAP_KIND_NORMALIZED) {
+    switch (env_variant()) {
+      case 1: return I8_LAUNCH(double, 6, 32, 64, 2, 2, true, double);
+      case 2: return I8_LAUNCH(double, 6, 80, 32, 1, 4, true, double);
+      case 3: return I8_LAUNCH(double, 6, 64, 64, 1, 3, true, double);
+      default: return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, double);
+    }
   }
+  return I8_LAUNCH(double, 6, 80, 64, 1, 2, false, double);
 }
 #undef I8_LAUNCH
 
