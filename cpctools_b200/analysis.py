@@ -83,6 +83,50 @@ def diff_transposed_device(t):
     return dt
 
 
+def _atom_tiles(x, bytes_per_atom: int):
+    """Atom ranges for HOST inputs that do not fit in HBM: every atom's time series is independent,
+    so a ``[F, A, D]`` trajectory is processed in atom tiles sized to ~40 % of the free device memory
+    (input tile + partial sums + results), results concatenated along the atom axis."""
+    n_atoms = int(x.shape[1])
+    if _device.is_tensor(x) and x.is_cuda:
+        return [(0, n_atoms)]
+    th = _device.require_cuda()
+    free, _ = th.cuda.mem_get_info()
+    per_tile = max(1, int(0.4 * free) // max(1, bytes_per_atom))
+    if per_tile >= n_atoms:
+        return [(0, n_atoms)]
+    return [(lo, min(n_atoms, lo + per_tile)) for lo in range(0, n_atoms, per_tile)]
+
+
+def _tiled(x, windows, kind, power, mult, returnDiff):
+    """Run the time-lag kernel over atom tiles of ``x``; returns per window ``t`` (and ``dt``) in the
+    container type of ``x``."""
+    th = _device.require_cuda()
+    F, D = int(x.shape[0]), int(x.shape[2])
+    itemsize = 4 if str(getattr(x, "dtype", "")).endswith("float32") else 8
+    per_atom = F * D * itemsize + F * 8 * (len(windows) + 1) * 8
+    tiles = _atom_tiles(x, per_atom)
+    if len(tiles) == 1:
+        X = _device.as_float_tensor(x)
+        return [_finish(t, x, returnDiff) for t in timelag_device(X, windows, kind, power, mult=mult)]
+    outs = [[] for _ in windows]
+    for lo, hi in tiles:
+        X = _device.as_float_tensor(x[:, lo:hi, :])
+        for k, t in enumerate(timelag_device(X, windows, kind, power, mult=mult)):
+            outs[k].append(_finish(t, x, returnDiff))
+        del X
+    res = []
+    for parts in outs:
+        if returnDiff:
+            if _device.is_tensor(x):
+                res.append((th.cat([p[0] for p in parts], dim=1), th.cat([p[1] for p in parts], dim=0)))
+            else:
+                res.append((np.concatenate([p[0] for p in parts], axis=1), np.concatenate([p[1] for p in parts], axis=0)))
+        else:
+            res.append(th.cat(parts, dim=1) if _device.is_tensor(x) else np.concatenate(parts, axis=1))
+    return res
+
+
 def _finish(t, like, returnDiff):
     if returnDiff:
         return _device.like_input(t, like), _device.like_input(diff_transposed_device(t), like)
@@ -106,9 +150,9 @@ def timeSOAP(
     """
     _validate(int(SOAPTrajectory.shape[0]), window, stride)
     kind, power = resolve_distance(distanceFunction)
-    X = _device.as_float_tensor(SOAPTrajectory)
-    (t,) = timelag_device(X, [window], kind, power)
-    return _finish(t, SOAPTrajectory, returnDiff)
+    if len(SOAPTrajectory.shape) != 3:
+        raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
+    return _tiled(SOAPTrajectory, [int(window)], kind, power, None, returnDiff)[0]
 
 
 def tempoSOAP(*args, **kwargs):
@@ -123,8 +167,9 @@ def timeSOAPsweep(SOAPTrajectory, windows=(1, 5, 10, 50), returnDiff: bool = Tru
     for w in windows:
         _validate(n_frames, int(w), None)
     kind, power = resolve_distance(distanceFunction)
-    X = _device.as_float_tensor(SOAPTrajectory)
-    return [_finish(t, SOAPTrajectory, returnDiff) for t in timelag_device(X, windows, kind, power)]
+    if len(SOAPTrajectory.shape) != 3:
+        raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
+    return _tiled(SOAPTrajectory, [int(w) for w in windows], kind, power, None, returnDiff)
 
 
 def timeSOAPfromCompressed(
@@ -158,11 +203,12 @@ def timeSOAPfromCompressed(
     kind, power = resolve_distance(distanceFunction)
     if kind == _lib.KIND_NORMALIZED:
         kind = _lib.KIND_NORMALIZED_FUSED
-    X = _device.as_float_tensor(soapFromdscribe)
-    mult = plan.multiplicity_device(X.dtype)
-    return [
-        _finish(t, soapFromdscribe, returnDiff) for t in timelag_device(X, windows, kind, power, mult=mult)
-    ]
+    if len(soapFromdscribe.shape) != 3:
+        raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
+    th = _device.require_cuda()
+    f32 = str(soapFromdscribe.dtype).endswith("float32")
+    mult = plan.multiplicity_device(th.float32 if f32 else th.float64)
+    return _tiled(soapFromdscribe, [int(w) for w in windows], kind, power, mult, returnDiff)
 
 
 def _simple_rows(X, window: int):

@@ -270,6 +270,22 @@ def test_timesoap_sweep_from_compressed_vs_oracle(S, F, A, species, dtype, windo
                 assert_allclose(eu, np.linalg.norm(X[1:] - X[:-1], axis=-1), rtol=1e-12, atol=1e-15)
 
 
+def test_host_trajectory_larger_than_budget_is_tiled_over_atoms(S, monkeypatch):
+    """host inputs that do not fit the device budget are processed in atom tiles (same results)."""
+    from cpctools_b200 import analysis
+
+    rng = np.random.default_rng(8)
+    X = O.normalizeArray(rng.random((20, 11, 64)))
+    monkeypatch.setattr(analysis, "_atom_tiles", lambda x, per_atom: [(0, 4), (4, 8), (8, 11)])
+    t, dt = S.timeSOAP(X, window=3)
+    want, wdt = O.timeSOAP_batched(X, window=3)
+    assert t.shape == want.shape and dt.shape == wdt.shape
+    assert_distance_parity(t, want, "f64")
+    assert_array_equal(dt, np.diff(t.T, axis=-1))
+    res = S.timeSOAPsweep(X, windows=(1, 2), returnDiff=False)
+    assert_distance_parity(res[1], O.timeSOAP_batched(X, window=2, returnDiff=False), "f64")
+
+
 def test_streaming_shortcut_matches_golden(S, golden):
     g = golden("timesoap")
     attrs1 = {"l_max": 8, "n_max": 8, "species": ["H"], "species_location_H-H": [0, 324]}
