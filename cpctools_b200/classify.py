@@ -170,6 +170,67 @@ def _prepared_blocks(SOAPTrajData, references: SOAPReferences, doNormalize: bool
         yield lo, hi, rows
 
 
+#: dictionaries up to this many references take the fused kernel (expansion folded into the references)
+FUSED_MAX_REFS = 32
+
+
+def _fused_setup(SOAPTrajData, references: SOAPReferences, kind: int):
+    """Device-side constants of ``soap_classify`` for this dataset / dictionary, or ``None`` when the
+    fused kernel does not apply (big dictionaries, kinds it does not implement)."""
+    th = _device.require_cuda()
+    spectra = np.asarray(references.spectra, dtype=np.float64)
+    K, Dref = spectra.shape
+    Dc = int(SOAPTrajData.shape[-1])
+    if K > FUSED_MAX_REFS or kind not in (_lib.KIND_SIMPLE, _lib.KIND_KERNEL, _lib.KIND_NORMALIZED):
+        return None
+    if (K + 1) * Dc * 8 > 200 * 1024:
+        return None
+    if Dc != Dref:  # compressed dataset: mono-species table (classify.py:151)
+        plan = getExpansionPlan(references.lmax, references.nmax)
+        if plan.d_compressed != Dc or plan.d_full != Dref:
+            raise ValueError("fillSOAPVectorFromdscribe: the given soap vector do not have the expected dimensions")
+        folded = np.stack([np.bincount(plan.index, weights=r, minlength=Dc) for r in spectra])
+        mult = th.from_numpy(plan.multiplicity.astype(np.float64)).cuda()
+    else:
+        folded, mult = spectra, None
+    return {
+        "refw": th.from_numpy(np.ascontiguousarray(folded)).cuda(),
+        "norm2": th.from_numpy(np.einsum("kd,kd->k", spectra, spectra)).cuda(),
+        "mult": mult, "K": K, "Dc": Dc,
+    }
+
+
+def _fused_blocks(SOAPTrajData, setup, kind, power, doNormalize, want_dist, frames: slice = None):
+    """Yield ``(lo, hi, dist[(hi-lo)*A, K] | None, amin, argmin)`` per streamed block, computed by the
+    fused kernel straight from the compressed rows."""
+    th = _device.require_cuda()
+    lib = _lib.load()
+    F, A = int(SOAPTrajData.shape[0]), int(SOAPTrajData.shape[1])
+    first, last, _ = (frames or slice(None)).indices(F)
+    Dc, K = setup["Dc"], setup["K"]
+    up = _Uploader(th)
+    budget_frames = max(1, (4 << 30) // max(1, A * Dc * 8))
+    for lo, hi in frame_ranges(SOAPTrajData, budget_frames):
+        lo, hi = max(lo, first), min(hi, last)
+        if lo >= hi:
+            continue
+        host = np.asarray(SOAPTrajData[lo:hi])
+        if host.dtype not in (np.float32, np.float64):
+            host = host.astype(np.float64)
+        rows = up.put(host).reshape(-1, Dc)
+        n = int(rows.shape[0])
+        dist = th.empty((n, K), dtype=th.float64, device="cuda") if want_dist else None
+        amin = th.empty(n, dtype=th.float64, device="cuda")
+        arg = th.empty(n, dtype=th.int32, device="cuda")
+        rc = lib.soap_classify(
+            rows.data_ptr(), None if setup["mult"] is None else setup["mult"].data_ptr(), setup["refw"].data_ptr(),
+            setup["norm2"].data_ptr(), n, Dc, K, kind, int(power), 1 if doNormalize else 0, _device.dtype_code(rows),
+            None if dist is None else dist.data_ptr(), arg.data_ptr(), amin.data_ptr(), _device.stream_ptr(),
+        )
+        _lib.check(rc, "soap_classify")
+        yield lo, hi, dist, amin, arg
+
+
 def getDistancesFromRef(SOAPTrajData, references: SOAPReferences, distanceCalculator: Callable, doNormalize: bool = False):
     """Distances between a SOAP-hdf5 trajectory and the given references (classify.py:120-160):
     ``float64[F, A, len(references)]`` (numpy)."""
@@ -186,6 +247,11 @@ def getDistancesFromInterval(SOAPTrajData, references: SOAPReferences, distanceC
     first, last, _ = (interval or slice(None)).indices(F)
     K = len(references)
     result = np.zeros((max(last - first, 0), A, K))
+    setup = _fused_setup(SOAPTrajData, references, kind)
+    if setup is not None:
+        for lo, hi, dist, _amin, _arg in _fused_blocks(SOAPTrajData, setup, kind, power, doNormalize, True, interval):
+            result[lo - first : hi - first] = _device.to_host(dist).reshape(hi - lo, A, K)
+        return result
     refs = None
     for lo, hi, rows in _prepared_blocks(SOAPTrajData, references, doNormalize, interval):
         if refs is None or refs.dtype != rows.dtype:
@@ -210,6 +276,12 @@ def applyClassification(SOAPTrajData, references: SOAPReferences, distanceCalcul
     F, A = int(SOAPTrajData.shape[0]), int(SOAPTrajData.shape[1])
     dist = np.zeros((F, A))
     ids = np.zeros((F, A), dtype=np.int64)
+    setup = _fused_setup(SOAPTrajData, references, kind)
+    if setup is not None:
+        for lo, hi, _dist, amin, arg in _fused_blocks(SOAPTrajData, setup, kind, power, doNormalize, False):
+            dist[lo:hi] = _device.to_host(amin).reshape(hi - lo, A)
+            ids[lo:hi] = _device.to_host(arg).reshape(hi - lo, A)
+        return SOAPclassification(dist, ids, references.names)
     refs = None
     for lo, hi, rows in _prepared_blocks(SOAPTrajData, references, doNormalize):
         if refs is None or refs.dtype != rows.dtype:

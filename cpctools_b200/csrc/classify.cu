@@ -1,0 +1,342 @@
+// classify.cu -- f1: distances from every (frame, atom) vector of a COMPRESSED SOAP dataset to a small
+// dictionary of reference spectra, with the fused arg-minimum of applyClassification.
+//
+// Reference semantics: getDistancesFromRef (src/SOAPify/classify.py:120-160: expand with the
+// mono-species table when the dataset is compressed, optionally normalise, then
+// getDistanceBetween(frame, references.spectra, f)) and applyClassification's argmin / amin over the
+// references (classify.py:274-275).
+//
+// Memory-bound GEMV-like work (K references, K small): the expansion is folded into the references --
+// with R'[k][i] = sum over the expanded slots j that gather compressed slot i of r_k[j], the dot of
+// the EXPANDED vector with r_k is x . R'_k -- and the norm of the expanded vector is the
+// multiplicity-weighted norm of the compressed one.  The kernel therefore reads Dc elements per
+// vector and nothing else: no expanded / normalised copy of the dataset ever exists.
+// One warp per vector, 128-bit streaming loads, R' and the multiplicities in shared memory,
+// K+1 warp reductions per vector, numpy's argmin rules (first NaN, then first minimum).
+#include "common.cuh"
+
+namespace soapb {
+
+constexpr int kClsThreads = 256;
+constexpr int kClsTK = 8;  // references handled per pass over a vector
+
+__device__ __forceinline__ bool cls_better(double v, int j, double bv, int bj) {
+  const bool vn = v != v, bn = bv != bv;
+  if (vn || bn) return vn && (!bn || j < bj);
+  return v < bv || (v == bv && j < bj);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kClsThreads, 2)
+    classify_kernel(const T *__restrict__ X, const double *__restrict__ mult, const double *__restrict__ refw,
+                    const double *__restrict__ ref_norm2, long long nvec, int D, int K, int kind, int power,
+                    int normalize_x, double *__restrict__ dist_out, int *__restrict__ argmin_out,
+                    double *__restrict__ min_out) {
+  extern __shared__ __align__(16) double smem_cls[];
+  double *sm_m = smem_cls;             // [D] multiplicities (1.0 when mult == NULL)
+  double *sm_r = smem_cls + D;         // [K][D] folded references
+  for (int i = threadIdx.x; i < D; i += kClsThreads) sm_m[i] = mult ? mult[i] : 1.0;
+  for (int i = threadIdx.x; i < K * D; i += kClsThreads) sm_r[i] = refw[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nwarps = (long long)gridDim.x * (kClsThreads / 32);
+  for (long long v = (long long)blockIdx.x * (kClsThreads / 32) + warp; v < nvec; v += nwarps) {
+    const T *x = X + (size_t)v * D;
+    double best_v = 0.0;
+    int best_j = -1;
+    double uu = 0.0;
+    for (int k0 = 0; k0 < K; k0 += kClsTK) {
+      const int kn = min(kClsTK, K - k0);
+      double acc[kClsTK], nn = 0.0;
+#pragma unroll
+      for (int k = 0; k < kClsTK; ++k) acc[k] = 0.0;
+      // four independent loads in flight per lane (the second and later passes hit L1/L2)
+      int i = lane;
+      for (; i + 96 < D; i += 128) {
+        double xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = (double)x[i + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = i + 32 * u;
+          nn = fma(xv[u] * sm_m[e], xv[u], nn);
+#pragma unroll
+          for (int k = 0; k < kClsTK; ++k)
+            if (k < kn) acc[k] = fma(xv[u], sm_r[(size_t)(k0 + k) * D + e], acc[k]);
+        }
+      }
+      for (; i < D; i += 32) {
+        const double xi = (double)x[i];
+        nn = fma(xi * sm_m[i], xi, nn);
+#pragma unroll
+        for (int k = 0; k < kClsTK; ++k)
+          if (k < kn) acc[k] = fma(xi, sm_r[(size_t)(k0 + k) * D + i], acc[k]);
+      }
+      if (k0 == 0) uu = warp_sum(nn);
+#pragma unroll
+      for (int k = 0; k < kClsTK; ++k) {
+        if (k >= kn) break;
+        const double uv = warp_sum(acc[k]);
+        const int j = k0 + k;
+        double d;
+        if (kind == SOAP_KIND_NORMALIZED) {
+          // SOAPdistanceNormalized on (optionally normalised) data: the reference spectra are used as given
+          const double nu = normalize_x ? ((uu == 0.0) ? 1.0 : sqrt(uu)) : 1.0;
+          d = sqrt(fabs(2.0 - 2.0 * (uv / nu)));
+        } else {
+          d = soap_epilogue(uv, uu, ref_norm2[j], kind, power);  // scale invariant in x
+        }
+        if (dist_out && lane == 0) dist_out[(size_t)v * K + j] = d;
+        if (best_j < 0 || cls_better(d, j, best_v, best_j)) { best_v = d; best_j = j; }
+      }
+    }
+    if (lane == 0) {
+      if (argmin_out) argmin_out[v] = best_j;
+      if (min_out) min_out[v] = best_v;
+    }
+  }
+}
+
+// ---- tiled variant: LANE = VECTOR ---------------------------------------------------------------
+// A CTA takes 32 consecutive vectors at a time.  Their rows (or a piece of them when the rows are
+// long) are dropped by the TMA engine into shared-memory slots 16*odd bytes apart, so that lane l
+// walks ITS OWN vector with conflict-free 128-bit loads while the folded references and the
+// multiplicities are read as warp-wide BROADCASTS (one wavefront for all 32 vectors).  No shuffle
+// reduction exists: a lane ends with the complete sums of its vector.  8 consumer warps split the
+// 16-byte units, warp 8 is the TMA producer, warp 9 sums the consumers' partials of a tile, applies
+// the distance and the arg-minimum and writes the results; tiles and partial-sum buffers are double
+// buffered and every hand-off is an mbarrier (no __syncthreads after the prologue).
+constexpr int kCtWarps = 8;
+constexpr int kCtThreads = (kCtWarps + 2) * 32;  // + TMA producer warp + finisher warp
+constexpr int kCtMaxK = 32;
+
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(kCtThreads, 1)
+    classify_tiled_kernel(const T *__restrict__ X, const double *__restrict__ mult, const double *__restrict__ refw,
+                          const double *__restrict__ ref_norm2, long long nvec, int D, int K, int kind, int power,
+                          int normalize_x, double *__restrict__ dist_out, int *__restrict__ argmin_out,
+                          double *__restrict__ min_out, int upp, int npieces, int stride) {
+  extern __shared__ __align__(128) unsigned char smem_ct[];
+  constexpr int UE = 16 / (int)sizeof(T);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Dp = npieces * upp * UE;                   // padded dimension (multiple of the unit)
+  unsigned char *stage0 = smem_ct;                     // [2][32 slots][stride]
+  double *sm_m = reinterpret_cast<double *>(smem_ct + (size_t)2 * 32 * stride);  // [Dp]
+  double *sm_r = sm_m + Dp;                            // [K][Dp]
+  double *red = sm_r + (size_t)K * Dp;                 // [2][kCtWarps][K+1][32]
+  const size_t red_elems = (size_t)kCtWarps * (K + 1) * 32;
+  uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * red_elems);
+  uint64_t *empty = full + 2, *red_full = full + 4, *red_empty = full + 6;
+
+  for (int i = tid; i < Dp; i += kCtThreads) sm_m[i] = i < D ? (mult ? mult[i] : 1.0) : 0.0;
+  for (int i = tid; i < K * Dp; i += kCtThreads) {
+    const int k = i / Dp, e = i - k * Dp;
+    sm_r[i] = e < D ? refw[(size_t)k * D + e] : 0.0;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kCtWarps);
+      mbar_init(&red_full[s], kCtWarps);
+      mbar_init(&red_empty[s], 1);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const long long ntiles = (nvec + 31) / 32;
+  const long long my_first = blockIdx.x;
+  if (warp == kCtWarps) {
+    // ===== producer: one bulk copy per vector row piece ===========================================
+    long long it = 0;
+    for (long long t = my_first; t < ntiles; t += gridDim.x) {
+      const int nv = (int)min(32LL, nvec - t * 32);
+      for (int p = 0; p < npieces; ++p, ++it) {
+        const int s = (int)(it & 1);
+        if (it >= 2) mbar_wait(&empty[s], (uint32_t)(((it >> 1) - 1) & 1));
+        const int e0 = p * upp * UE;
+        const uint32_t pbytes = (uint32_t)(min(D - e0, upp * UE) * (int)sizeof(T));
+        if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nv * pbytes);
+        __syncwarp();
+        if (lane < nv)
+          bulk_g2s(stage0 + ((size_t)s * 32 + lane) * stride, X + (size_t)(t * 32 + lane) * D + e0, pbytes, &full[s]);
+      }
+    }
+  } else if (warp == kCtWarps + 1) {
+    // ===== finisher: sums of the consumers' partials -> distances, arg-minimum, results ===========
+    long long tcount = 0;
+    for (long long t = my_first; t < ntiles; t += gridDim.x, ++tcount) {
+      const int rb = (int)(tcount & 1);
+      mbar_wait(&red_full[rb], (uint32_t)((tcount >> 1) & 1));
+      const double *r = red + rb * red_elems;
+      const long long v = t * 32 + lane;
+      double uu = 0.0;
+      for (int w = 0; w < kCtWarps; ++w) uu += r[((size_t)w * (K + 1)) * 32 + lane];
+      double best_v = 0.0;
+      int best_j = -1;
+      for (int k = 0; k < K; ++k) {
+        double uv = 0.0;
+        for (int w = 0; w < kCtWarps; ++w) uv += r[((size_t)w * (K + 1) + k + 1) * 32 + lane];
+        double d;
+        if (kind == SOAP_KIND_NORMALIZED) {
+          const double nu = normalize_x ? ((uu == 0.0) ? 1.0 : sqrt(uu)) : 1.0;
+          d = sqrt(fabs(2.0 - 2.0 * (uv / nu)));
+        } else {
+          d = soap_epilogue(uv, uu, ref_norm2[k], kind, power);
+        }
+        if (v < nvec && dist_out) dist_out[(size_t)v * K + k] = d;
+        if (best_j < 0 || cls_better(d, k, best_v, best_j)) { best_v = d; best_j = k; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&red_empty[rb]);
+      if (v < nvec) {
+        if (argmin_out) argmin_out[v] = best_j;
+        if (min_out) min_out[v] = best_v;
+      }
+    }
+  } else {
+    // ===== consumers ================================================================================
+    const uint32_t st_addr = smem_u32(stage0), m_addr = smem_u32(sm_m), r_addr = smem_u32(sm_r);
+    long long it = 0, tcount = 0;
+    for (long long t = my_first; t < ntiles; t += gridDim.x) {
+      double acc[KMAX + 1];  // statically indexed everywhere: stays in registers
+#pragma unroll
+      for (int q = 0; q <= KMAX; ++q) acc[q] = 0.0;
+      for (int p = 0; p < npieces; ++p, ++it) {
+        const int s = (int)(it & 1);
+        const int e0 = p * upp * UE;
+        const int punits = (min(D - e0, upp * UE) + UE - 1) / UE;
+        mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));
+        const uint32_t xrow = st_addr + (uint32_t)((s * 32 + lane) * stride);
+        for (int u = warp; u < punits; u += kCtWarps) {
+          double x0, x1;
+          if constexpr (sizeof(T) == 8) {
+            const double2 xv = lds_d2(xrow + 16u * u);
+            x0 = xv.x; x1 = xv.y;
+            const uint32_t eo = (uint32_t)(e0 + 2 * u) * 8u;
+            const double2 mv = lds_d2(m_addr + eo);
+            acc[0] = fma(x0 * mv.x, x0, acc[0]);
+            acc[0] = fma(x1 * mv.y, x1, acc[0]);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k < K) {
+                const double2 rv = lds_d2(r_addr + (uint32_t)k * (uint32_t)Dp * 8u + eo);
+                acc[k + 1] = fma(x0, rv.x, acc[k + 1]);
+                acc[k + 1] = fma(x1, rv.y, acc[k + 1]);
+              }
+            }
+          } else {
+            const float4 xv = lds_f4(xrow + 16u * u);
+            const double xs[4] = {(double)xv.x, (double)xv.y, (double)xv.z, (double)xv.w};
+            const uint32_t eo = (uint32_t)(e0 + 4 * u) * 8u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const double2 mv = lds_d2(m_addr + eo + 16u * h);
+              acc[0] = fma(xs[2 * h] * mv.x, xs[2 * h], acc[0]);
+              acc[0] = fma(xs[2 * h + 1] * mv.y, xs[2 * h + 1], acc[0]);
+            }
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+              if (k < K) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const double2 rv = lds_d2(r_addr + (uint32_t)k * (uint32_t)Dp * 8u + eo + 16u * h);
+                  acc[k + 1] = fma(xs[2 * h], rv.x, acc[k + 1]);
+                  acc[k + 1] = fma(xs[2 * h + 1], rv.y, acc[k + 1]);
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      // hand the K+1 partial sums of every vector to the finisher warp
+      const int rb = (int)(tcount & 1);
+      if (tcount >= 2) mbar_wait(&red_empty[rb], (uint32_t)(((tcount >> 1) - 1) & 1));
+      double *r = red + rb * red_elems;
+#pragma unroll
+      for (int q = 0; q <= KMAX; ++q)
+        if (q <= K) r[((size_t)warp * (K + 1) + q) * 32 + lane] = acc[q];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&red_full[rb]);
+      ++tcount;
+    }
+  }
+}
+
+}  // namespace soapb
+
+using namespace soapb;
+
+extern "C" int soap_classify(const void *X, const void *mult, const double *refw, const double *ref_norm2,
+                             int64_t nvec, int dim, int n_refs, int kind, int power, int normalize_x, int dtype,
+                             double *dist_out, int32_t *argmin_out, double *min_out, void *stream) {
+  SOAP_REQUIRE(nvec >= 0 && dim > 0 && n_refs > 0, "soap_classify: bad shape");
+  if (nvec == 0) return SOAP_OK;
+  SOAP_REQUIRE(X && refw, "soap_classify: null input");
+  SOAP_REQUIRE(dist_out || argmin_out || min_out, "soap_classify: no output requested");
+  SOAP_REQUIRE(kind == SOAP_KIND_NORMALIZED || ref_norm2 != nullptr, "soap_classify: reference norms are required for this kind");
+  SOAP_REQUIRE(kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL || kind == SOAP_KIND_NORMALIZED,
+               "soap_classify: kind %d", kind);
+  auto s = static_cast<cudaStream_t>(stream);
+  {
+    // tiled lane=vector kernel: rows must be 16-byte multiples; references + two tile stages must fit
+    const int es = dtype == SOAP_F64 ? 8 : 4, ue = 16 / es;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (((size_t)dim * es) % 16 == 0);
+    const int n_units = (dim + ue - 1) / ue;
+    const size_t budget = (size_t)max_smem_optin() - 2048;
+    if (aligned && n_refs <= kCtMaxK && (dtype == SOAP_F64 || dtype == SOAP_F32)) {
+      for (int npieces = 1; npieces <= n_units; ++npieces) {
+        const int upp = (n_units + npieces - 1) / npieces;
+        const int real_pieces = (n_units + upp - 1) / upp;
+        const int stride = 16 * (upp | 1);
+        const size_t Dp = (size_t)real_pieces * upp * ue;
+        const size_t fixed = (size_t)(n_refs + 1) * Dp * 8 + (size_t)2 * kCtWarps * (n_refs + 1) * 32 * 8 + 128;
+        const size_t smem_t = (size_t)2 * 32 * stride + fixed;
+        if (fixed + 2 * 32 * 16 * 3 > budget) break;
+        if (smem_t > budget) continue;
+        const long long ntiles = (nvec + 31) / 32;
+        const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
+        ProfScope prof(SOAP_PROF_PAIRS, s);
+#define CT_LAUNCH(T, KM)                                                                                              \
+  do {                                                                                                                \
+    SOAP_CUDA(cudaFuncSetAttribute(classify_tiled_kernel<T, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+    classify_tiled_kernel<T, KM><<<grid, kCtThreads, smem_t, s>>>(                                                    \
+        static_cast<const T *>(X), static_cast<const double *>(mult), refw, ref_norm2, nvec, dim, n_refs, kind, power, \
+        normalize_x, dist_out, argmin_out, min_out, upp, real_pieces, stride);                                        \
+  } while (0)
+        if (dtype == SOAP_F64) {
+          if (n_refs <= 8) CT_LAUNCH(double, 8); else if (n_refs <= 16) CT_LAUNCH(double, 16); else CT_LAUNCH(double, 32);
+        } else {
+          if (n_refs <= 8) CT_LAUNCH(float, 8); else if (n_refs <= 16) CT_LAUNCH(float, 16); else CT_LAUNCH(float, 32);
+        }
+#undef CT_LAUNCH
+        return check_launch("classify_tiled_kernel");
+      }
+    }
+  }
+  const size_t smem = (size_t)(n_refs + 1) * dim * sizeof(double);
+  if (smem > (size_t)max_smem_optin() - 1024)
+    return set_error(SOAP_EUNSUPPORTED, "soap_classify: %d references of dimension %d do not fit in shared memory; use soap_pairs",
+                     n_refs, dim);
+  int per_sm = (int)((size_t)(max_smem_optin() - 2048) / (smem + 1024));  // latency hiding comes from resident warps
+  per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+  const long long want = (nvec + kClsThreads / 32 - 1) / (kClsThreads / 32);
+  const int grid = (int)(want < (long long)num_sms() * per_sm ? want : (long long)num_sms() * per_sm);
+  ProfScope prof(SOAP_PROF_PAIRS, s);
+  if (dtype == SOAP_F64) {
+    SOAP_CUDA(cudaFuncSetAttribute(classify_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    classify_kernel<double><<<grid, kClsThreads, smem, s>>>(static_cast<const double *>(X), static_cast<const double *>(mult),
+                                                            refw, ref_norm2, nvec, dim, n_refs, kind, power, normalize_x,
+                                                            dist_out, argmin_out, min_out);
+  } else if (dtype == SOAP_F32) {
+    SOAP_CUDA(cudaFuncSetAttribute(classify_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    classify_kernel<float><<<grid, kClsThreads, smem, s>>>(static_cast<const float *>(X), static_cast<const double *>(mult),
+                                                           refw, ref_norm2, nvec, dim, n_refs, kind, power, normalize_x,
+                                                           dist_out, argmin_out, min_out);
+  } else {
+    return set_error(SOAP_EUNSUPPORTED, "soap_classify: dtype %d", dtype);
+  }
+  return check_launch("classify_kernel");
+}

@@ -109,6 +109,17 @@ __device__ __forceinline__ void stg_stream16(void *p, const int4 &v) {
                : "memory");
 }
 
+// ---- shared-memory access by 32-bit address (keeps the hot loop free of 64-bit pointer math) ----
+__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

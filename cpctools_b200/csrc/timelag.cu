@@ -77,17 +77,6 @@ static bool make_plan(int D, int elem_size, const int *windows, int nw, TimelagP
   return false;
 }
 
-// ---- shared-memory access by 32-bit address (keeps the hot loop free of 64-bit pointer math) ----
-__device__ __forceinline__ double2 lds_d2(uint32_t addr) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ void cp_async_elem(uint32_t dst, const void *src, int bytes) {
   if (bytes == 8)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");

@@ -122,6 +122,19 @@ int soap_pairs(const void *data, const void *spectra, void *out, int64_t n_data,
                int dim, int64_t ldo, int kind, int power, int dtype, int path, int32_t *argmin_out,
                double *min_out, void *scratch, void *stream);
 
+/* ---- classification against a small dictionary: getDistancesFromRef, classify.py:120-160, and
+ * applyClassification's argmin / amin, classify.py:274-275, fused and straight from COMPRESSED data.
+ * X[nvec][dim] (dtype); mult[dim] doubles = slot multiplicities of the mono-species gather table
+ * (NULL = 1: data already expanded); refw[n_refs][dim] doubles = reference spectra FOLDED onto the
+ * compressed slots (refw[k][i] = sum of r_k[j] over the expanded slots j that gather slot i; the
+ * spectra themselves when nothing is compressed); ref_norm2[n_refs] = |r_k|^2 (needed by SIMPLE /
+ * KERNEL).  normalize_x != 0 reproduces doNormalize=True for SOAP_KIND_NORMALIZED (zero norm -> 1).
+ * Outputs (any subset): dist_out[nvec][n_refs], argmin_out[nvec], min_out[nvec]; all float64 / int32.
+ */
+int soap_classify(const void *X, const void *mult, const double *refw, const double *ref_norm2, int64_t nvec,
+                  int dim, int n_refs, int kind, int power, int normalize_x, int dtype, double *dist_out,
+                  int32_t *argmin_out, double *min_out, void *stream);
+
 /* ---- synthetic data for the benchmarks (counter-based hash RNG, reproducible) ------------
  * fills n elements of `dtype` with uniform [0,1) values derived from (seed, element index).
  */

@@ -117,6 +117,27 @@ def main():
         report("timelag(compressed)", "2000x2472x324 f64 windows=(1,)", ms, X.numel() * 8)
         del X
 
+    # ---- classification against a small dictionary (f1): fused kernel straight from compressed rows
+    if want("classify"):
+        import ctypes
+        F, A, K = (50, 20000, 8) if args.quick else (200, 50000, 8)
+        for Dc, Df, kw in ((324, 576, {}),):
+            raw = fill((F * A, Dc), torch.float64)
+            plan = S.getExpansionPlan(8, 8)
+            refs = np.random.default_rng(0).random((K, Df))
+            refs /= np.linalg.norm(refs, axis=-1, keepdims=True)
+            folded = torch.from_numpy(np.stack([np.bincount(plan.index, weights=r, minlength=Dc) for r in refs])).cuda()
+            norm2 = torch.ones(K, dtype=torch.float64, device="cuda")
+            mult = plan.multiplicity_device(torch.float64)
+            amin = torch.empty(F * A, dtype=torch.float64, device="cuda")
+            arg = torch.empty(F * A, dtype=torch.int32, device="cuda")
+            lib = _lib.load()
+            fn = lambda: _lib.check(lib.soap_classify(raw.data_ptr(), mult.data_ptr(), folded.data_ptr(), norm2.data_ptr(), F * A, Dc, K,
+                                                      _lib.KIND_NORMALIZED, 1, 1, _lib.F64, None, arg.data_ptr(), amin.data_ptr(), None))
+            ms, _ = timed(fn, _lib.PROF_PAIRS)
+            report("classify(fused)", f"{F}x{A} Dc{Dc} K={K} f64 argmin", ms, F * A * (Dc * 8 + 12), vec_per_s=F * A / ms * 1e3)
+            del raw
+
     # ---- pair kernels (all-pairs matrix, configs[3]: D = 576)
     if want("pairs"):
         N = 8192 if args.quick else 25000

@@ -355,6 +355,60 @@ def test_classification_matches_golden(S, golden):
     assert_distance_parity(part, g["cls_dist"][20:57], "f64")
 
 
+def test_classification_fused_and_unfused_paths_agree(S, golden, monkeypatch):
+    """the fused kernel (expansion folded into the references) against the two-kernel path and the
+    oracle, for all three distance kinds, normalised or not, f64 and f32 data."""
+    from cpctools_b200 import classify
+
+    g = golden("classify")
+    attrs = {"l_max": 8, "n_max": 8, "species": ["Au"], "species_location_Au-Au": [0, 324]}
+    refs = S.SOAPReferences(["a", "b", "c", "d"], g["cls_ref_spectra"], 8, 8)
+    orefs = type("R", (), {"names": refs.names, "spectra": refs.spectra, "lmax": 8, "nmax": 8, "__len__": lambda self: 4})()
+    K = _kinds(S)
+    for dtype, path in ((np.float64, "f64"), (np.float32, "f32")):
+        raw = g["cls_raw"][:40].astype(dtype)
+        ds = FakeSOAPDataset(raw, 16, attrs)
+        for name, norm in (("normalized", True), ("simple", False), ("kernel2", False), ("simple", True)):
+            fn, okind, power = K[name]
+            ofn = {"normalized": O.SOAPdistanceNormalized, "simple": O.simpleSOAPdistance,
+                   "kernel2": lambda a, b: O.SOAPdistance(a, b, 2)}[name]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = O.getDistancesFromRef(FakeSOAPDataset(raw.astype(np.float64), 16, attrs), orefs, ofn, doNormalize=norm)
+            fused = S.getDistancesFromRef(ds, refs, fn, doNormalize=norm)
+            assert_distance_parity(fused, want, path, what=f"fused {name} {dtype.__name__}")
+            cl = S.applyClassification(ds, refs, fn, doNormalize=norm)
+            assert_array_equal(cl.references, np.argmin(fused, axis=-1))
+            assert_array_equal(cl.distances, np.amin(fused, axis=-1))
+            monkeypatch.setattr(classify, "FUSED_MAX_REFS", 0)  # force the expand -> normalise -> pairs path
+            unfused = S.getDistancesFromRef(ds, refs, fn, doNormalize=norm)
+            monkeypatch.setattr(classify, "FUSED_MAX_REFS", 32)
+            assert_distance_parity(unfused, want, path, what=f"unfused {name} {dtype.__name__}")
+
+
+@pytest.mark.parametrize("nmax,lmax,K", [(8, 8, 1), (8, 8, 9), (8, 8, 20), (8, 8, 32), (8, 8, 40), (5, 2, 6), (1, 0, 3)])
+def test_classification_shapes_vs_oracle(S, nmax, lmax, K):
+    """dictionary sizes across the kernel's register variants (<= 8 / 16 / 32 references), beyond them
+    (two-kernel path), rows that are not 16-byte multiples (warp-per-vector kernel), several tiles."""
+    rng = np.random.default_rng(nmax * 100 + lmax * 10 + K)
+    dc = (lmax + 1) * nmax * (nmax + 1) // 2
+    raw = synthetic_soap((23, 19, dc), seed=K, kind="W")
+    attrs = {"l_max": lmax, "n_max": nmax, "species": ["Au"], "species_location_Au-Au": [0, dc]}
+    ds = FakeSOAPDataset(raw, 7, attrs)
+    spectra = O.normalizeArray(rng.random((K, (lmax + 1) * nmax * nmax)))
+    refs = S.SOAPReferences([f"r{k}" for k in range(K)], spectra, lmax, nmax)
+    orefs = type("R", (), {"names": refs.names, "spectra": spectra, "lmax": lmax, "nmax": nmax, "__len__": lambda self: K})()
+    if dc == (lmax + 1) * nmax * nmax:  # nMax = 1: nothing to expand, the dataset is used as it is
+        assert dc == 1
+    want = O.getDistancesFromRefNormalized(ds, orefs)
+    got = S.getDistancesFromRefNormalized(ds, refs)
+    assert got.shape == want.shape == (23, 19, K)
+    assert_distance_parity(got, want, "f64", what=f"n{nmax} l{lmax} K{K}")
+    cl = S.applyClassification(ds, refs, S.SOAPdistanceNormalized, doNormalize=True)
+    assert_array_equal(cl.references, np.argmin(got, axis=-1))
+    assert_array_equal(cl.distances, np.amin(got, axis=-1))
+
+
 def test_argmin_numpy_rules(S):
     """ties -> first index; NaN -> first NaN (numpy.argmin / amin, classify.py:274-275)."""
     import torch
