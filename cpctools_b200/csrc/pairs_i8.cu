@@ -45,6 +45,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// distance from the exact dot g and the reciprocal norms (rr = 1/|x| * 1/|y|) for the kinds that
+// normalise inside: SIMPLE mirrors scipy's clipped cosine (distances.py:18,33), KERNEL distances.py:51,66
+__device__ __forceinline__ double fast_cosine_distance(double g, double rr, int kind, int power) {
+  const double c = g * rr;
+  if (kind == SOAP_KIND_SIMPLE) {
+    double cosd = 1.0 - c;
+    cosd = (cosd != cosd) ? cosd : fmin(fmax(cosd, 0.0), 2.0);
+    return sqrt(2.0 - 2.0 * (1.0 - cosd));
+  }
+  return sqrt(2.0 - 2.0 * ipow(c, power));
+}
+
 // ---- pre-pass: row scale, digit planes (zero padded to Dp), squared row norms ----------------------
 // planes[a][row][k] int8; scale[row] = sigma * 2^(8(ND-1)) so that  x.y = scale_i scale_j sum_g S_g 2^(-8g)
 template <typename T, int ND>
@@ -135,6 +147,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
   uint64_t *tmem_full = bars + 2 * STAGES, *tmem_empty = tmem_full + ACC;
   uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + ACC);
   int *col_exp = reinterpret_cast<int *>(smem + (size_t)STAGES * STAGE_BYTES + 256);  // [kI8EpiWarps][BN] (FAST path)
+  double *col_rn = reinterpret_cast<double *>(col_exp + kI8EpiWarps * BN);            // [kI8EpiWarps][BN], cosine kinds only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tiles = (long long)tiles_m * tiles_n;
@@ -243,9 +256,13 @@ __global__ void __launch_bounds__(kI8Threads, 1)
         const bool row_ok = row < M;
         const int ei = row_ok ? ((__double2hiint(sa[row]) >> 20) & 0x7ff) : 0x7ff;
         int *my_exp = col_exp + (warp - 2) * BN;
+        double *my_rn = col_rn + (warp - 2) * BN;
+        const bool cosine = (kind != SOAP_KIND_NORMALIZED);
+        const double ri = (cosine && row_ok) ? rsqrt(uu[row]) : 1.0;  // 1/|x_i|; a zero vector gives inf -> NaN like 0/0
         for (int cidx = lane; cidx < BN; cidx += 32) {
           const long long col = (long long)tn * BN + cidx;
           my_exp[cidx] = col < N ? ((__double2hiint(sb[col]) >> 20) & 0x7ff) : 0x7ff;
+          if (cosine) my_rn[cidx] = col < N ? rsqrt(vv[col]) : 1.0;
         }
         __syncwarp();
         mbar_wait_guard(&tmem_full[as], (uint32_t)((it / ACC) & 1));
@@ -278,7 +295,11 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                 int k = ei + ej[jj] - 2 * 1023;
                 k = k < -126 ? -126 : (k > 127 ? 127 : k);
                 const float pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __int_as_float(0x7fc00000) : __int_as_float((k + 127) << 23);
-                asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
+                if (cosine) {
+                  o[k4] = (float)fast_cosine_distance((double)(tf * pw), ri * my_rn[c * 16 + jj], kind, power);
+                } else {
+                  asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
+                }
               }
               if (row_ok) {
                 if (vec4 && col0 + j + 4 <= N) {
@@ -327,7 +348,8 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                 k = k < -1022 ? -1022 : (k > 1023 ? 1023 : k);
                 const double pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __longlong_as_double(0x7ff8000000000000ll)
                                                                    : __hiloint2double((k + 1023) << 20, 0);
-                o[k2] = sqrt(fabs(fma(-2.0, tsum * pw, 2.0)));
+                o[k2] = cosine ? fast_cosine_distance(tsum * pw, ri * my_rn[c * 8 + jj], kind, power)
+                               : sqrt(fabs(fma(-2.0, tsum * pw, 2.0)));
               }
               if (row_ok) {
                 if (vec2 && col0 + j + 2 <= N) {
@@ -468,7 +490,10 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   const int tiles_m = (int)((M + kI8BM - 1) / kI8BM), tiles_n = (int)((N + BN - 1) / BN);
   const long long tiles = (long long)tiles_m * tiles_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  constexpr size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)kI8EpiWarps * BN * 4;
+  // the reciprocal-norm staging only exists for the cosine kinds (it would not fit beside 4 stages)
+  const size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)kI8EpiWarps * BN * 4 +
+                      ((FAST && kind != SOAP_KIND_NORMALIZED) ? (size_t)kI8EpiWarps * BN * 8 : 0);
+  SOAP_REQUIRE(SMEM <= (size_t)max_smem_optin(), "soap_pairs: internal: tile configuration exceeds shared memory");
   auto kern = pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, OutT>;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   ProfScope prof(SOAP_PROF_PAIRS, s);
@@ -493,6 +518,7 @@ size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
 
 int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
+  if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, float);
   if (kind == SOAP_KIND_NORMALIZED) {
     // measured on 25 000^2 x 576 (ms): N160/K64/4 stages 2.19 | N80/K64/4 stages, 2 acc. sets 2.33 |
     // N160/K128/2 stages 2.35 | N80/K128/2 stages, 2 acc. sets 2.41
@@ -508,6 +534,7 @@ int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t 
 
 int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
+  if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, double);
   if (kind == SOAP_KIND_NORMALIZED) {
     switch (env_variant()) {
       case 1: return I8_LAUNCH(double, 6, 32, 64, 2, 2, true, double);
