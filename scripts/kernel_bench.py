@@ -112,6 +112,16 @@ def main():
         ms, _ = timed(lambda: timelag_device(X, (1,), _lib.KIND_EUCLID, 1), _lib.PROF_TIMELAG)
         report("timelag(euclid)", f"{F}x{A // 2}x1728 f64 windows=(1,)", ms, X.numel() * 8 + (F - 1) * (A // 2) * 8)
         del X
+        # configs[4]: raw quippy rows, 3 species nMax = lMax = 6 (1198 columns), composed table
+        from oracle.fake_dataset import dscribe_attrs
+        attrs, dcq = dscribe_attrs(6, 6, ["H", "C", "O"])
+        slq = {k[len("species_location_"):].replace("-", ""): slice(*v) for k, v in attrs.items() if k.startswith("species_location_")}
+        planq = S.getExpansionPlan(6, 6, ["H", "C", "O"], slq, quippy=True)
+        for dt, es in ((torch.float64, 8), (torch.float32, 4)):
+            Xq = fill((1000, 4096, dcq + 1), dt)
+            ms, _ = timed(lambda: timelag_device(Xq, (1,), _lib.KIND_SIMPLE, 1, mult=planq.multiplicity_device(dt)), _lib.PROF_TIMELAG)
+            report("timelag(quippy raw)", f"1000x4096x1198 {dt} windows=(1,)", ms, Xq.numel() * es + 999 * 4096 * 8)
+            del Xq
         X = fill((2000, 309 * 8, 324), torch.float64)
         ms, _ = timed(lambda: timelag_device(X, (1,), _lib.KIND_SIMPLE, 1, mult=S.getExpansionPlan(8, 8).multiplicity_device(torch.float64)), _lib.PROF_TIMELAG)
         report("timelag(compressed)", "2000x2472x324 f64 windows=(1,)", ms, X.numel() * 8)

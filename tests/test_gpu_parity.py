@@ -286,6 +286,46 @@ def test_host_trajectory_larger_than_budget_is_tiled_over_atoms(S, monkeypatch):
     assert_distance_parity(res[1], O.timeSOAP_batched(X, window=2, returnDiff=False), "f64")
 
 
+def test_config1_shape_against_the_loop_oracle(S):
+    """BASELINE configs[0]: 309 atoms x 200 frames, 1 species (Dc 324 -> Df 576), fp64, the reference's
+    own Python-loop path (oracle port) as the checker, default distance and SOAPdistanceNormalized."""
+    raw = synthetic_soap((200, 309, 324), seed=12345, kind="U")
+    X = O.normalizeArray(O.fillSOAPVectorFromdscribe(raw, 8, 8))
+    Xg = S.normalizeArray(S.fillSOAPVectorFromdscribe(raw, 8, 8))
+    assert_allclose(Xg, X, rtol=1e-12, atol=0)
+    t, dt = S.timeSOAP(Xg, window=1)
+    want_t, want_dt = O.timeSOAP(X, window=1)  # Python double loop + scipy cosine
+    assert t.shape == (199, 309) and dt.shape == (309, 198)
+    assert_distance_parity(t, want_t, "f64", what="config1 simple")
+    assert_allclose(dt, want_dt, rtol=0, atol=1e-11)
+    tn = S.timeSOAP(Xg, window=1, returnDiff=False, distanceFunction=S.SOAPdistanceNormalized)
+    assert_distance_parity(tn, O.timeSOAP(X, window=1, returnDiff=False, distanceFunction=O.SOAPdistanceNormalized), "f64")
+    (tc,) = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1,), returnDiff=False)
+    assert_distance_parity(tc, want_t, "f64", what="config1 fused")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_config5_quippy_three_species_fused(S, dtype):
+    """BASELINE configs[4]: raw quippy rows (3 species, nMax = lMax = 6: 1198 columns incl. the trailing
+    covariance column, quippy slot order) -> timeSOAP without materialising anything, fp64 and fp32
+    (fp32 rows are not 16-byte multiples: cp.async staging path)."""
+    sp = ["H", "C", "O"]
+    attrs, dc = dscribe_attrs(6, 6, sp)
+    sl = _slices_from_attrs(attrs)
+    raw = synthetic_soap((45, 7, dc + 1), seed=3, kind="W", dtype=dtype)
+    addr = O.getAddressesQuippyLikeDscribe(6, 6, sp)
+    permuted = raw.astype(np.float64)[..., :dc][..., addr]            # engine.py:226,260
+    X = O.normalizeArray(O.fillSOAPVectorFromdscribe(permuted, 6, 6, sp, sl))
+    path = "f64" if dtype == np.float64 else "f32"
+    got = S.timeSOAPfromCompressed(raw, 6, 6, ["O", "H", "C"], sl, windows=(1, 10), quippy=True)
+    for w, (t, dt) in zip((1, 10), got):
+        want, wdt = O.timeSOAP_batched(X, window=w)
+        assert t.shape == want.shape and dt.shape == wdt.shape
+        assert_distance_parity(t, want, path, what=f"quippy w{w}")
+    full = S.fillSOAPVectorFromQuip(raw, 6, 6, sp, sl)
+    assert_array_equal(full, O.fillSOAPVectorFromdscribe(raw[..., :dc][..., addr], 6, 6, sp, sl))
+
+
 def test_streaming_shortcut_matches_golden(S, golden):
     g = golden("timesoap")
     attrs1 = {"l_max": 8, "n_max": 8, "species": ["H"], "species_location_H-H": [0, 324]}
