@@ -11,7 +11,8 @@ from .utils import *  # noqa: F401,F403
 from .distances import *  # noqa: F401,F403
 from .analysis import *  # noqa: F401,F403
 from .classify import *  # noqa: F401,F403
-from . import utils, distances, analysis, classify, streaming  # noqa: F401
+from .transitions import *  # noqa: F401,F403
+from . import utils, distances, analysis, classify, streaming, transitions  # noqa: F401
 from ._lib import SoapB200Error, build_library, launch_count  # noqa: F401
 
 __version__ = "0.1.0"

@@ -16,7 +16,7 @@ from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libsoapb200.so")
-SOURCES = ("capi.cu", "expand.cu", "timelag.cu", "pairs.cu", "pairs_dmma.cu", "pairs_tf32.cu", "pairs_i8.cu", "classify.cu")
+SOURCES = ("capi.cu", "expand.cu", "timelag.cu", "pairs.cu", "pairs_dmma.cu", "pairs_tf32.cu", "pairs_i8.cu", "classify.cu", "transitions.cu")
 NVCC_FLAGS = (
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--threads", "0",
@@ -46,6 +46,7 @@ SIGNATURES = {
                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "soap_classify": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
+    "soap_transition_counts": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "soap_fill_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_int, c_void_p]),
 }
 

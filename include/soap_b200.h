@@ -135,6 +135,15 @@ int soap_classify(const void *X, const void *mult, const double *refw, const dou
                   int dim, int n_refs, int kind, int power, int normalize_x, int dtype, double *dist_out,
                   int32_t *argmin_out, double *min_out, void *stream);
 
+/* ---- transition counts of a classification: transitionMatrixFromSOAPClassification,
+ * transitions/__init__.py:9-48.  states[n_frames][n_atoms] int32 (class index per frame and atom);
+ * counts[n_classes][n_classes] uint64 is zeroed and then
+ *     counts[states[f-window][a]][states[f][a]] += 1   for f in range(window, n_frames, stride), all a.
+ * Entries outside [0, n_classes) are skipped.  Bit-exact.
+ */
+int soap_transition_counts(const int32_t *states, int64_t n_frames, int64_t n_atoms, int n_classes, int64_t window,
+                           int64_t stride, uint64_t *counts, void *stream);
+
 /* ---- synthetic data for the benchmarks (counter-based hash RNG, reproducible) ------------
  * fills n elements of `dtype` with uniform [0,1) values derived from (seed, element index).
  */

@@ -210,6 +210,20 @@ def gen_classify(S):
     return out
 
 
+def gen_transitions(S):
+    """transition matrices of random classifications (transitions/__init__.py:9-97)."""
+    out = {}
+    rng = np.random.default_rng(12345)
+    refs = rng.integers(0, 5, size=(60, 17))
+    out["refs"] = refs
+    data = S.SOAPclassification(np.zeros(refs.shape), refs, ["a", "b", "c", "d", "e"])
+    for stride, window in ((1, None), (1, 5), (3, 3), (2, 7), (1, 59), (1, 60)):
+        tag = f"s{stride}_w{window}"
+        out["tm_" + tag] = S.transitionMatrixFromSOAPClassification(data, stride, window)
+        out["tmn_" + tag] = S.transitionMatrixFromSOAPClassificationNormalized(data, stride, window)
+    return out
+
+
 def main() -> int:
     S = load_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -219,6 +233,7 @@ def main() -> int:
         ("math", gen_math),
         ("timesoap", gen_timesoap),
         ("classify", gen_classify),
+        ("transitions", gen_transitions),
     ):
         data = fn(S)
         path = os.path.join(GOLDEN_DIR, name + ".npz")

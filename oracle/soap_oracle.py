@@ -340,6 +340,36 @@ def applyClassification(SOAPTrajData, references, distanceCalculator, doNormaliz
 
 
 # --------------------------------------------------------------------------------------
+# transition matrix of a classification (src/SOAPify/transitions/__init__.py:9-97)
+# --------------------------------------------------------------------------------------
+
+
+def transitionMatrixFromSOAPClassification(references, n_classes, stride=1, window=None):
+    """Counts of (state[f-window], state[f]) over f in range(window, F, stride) and all atoms
+    (transitions/__init__.py:9-48); ``references`` is the int[F, A] array of a SOAPclassification."""
+    if window is None:
+        window = stride
+    if window < stride:
+        raise ValueError("the window must be bigger than the stride")
+    if window > references.shape[0]:
+        raise ValueError("stride and window must be smaller than simulation lenght")
+    mat = np.zeros((n_classes, n_classes), dtype=np.float64)
+    for f in range(window, references.shape[0], stride):
+        np.add.at(mat, (references[f - window], references[f]), 1)
+    return mat
+
+
+def normalizeMatrixByRow(transMat):
+    """Rows summing to 1, empty rows left at zero (transitions/__init__.py:51-69)."""
+    out = transMat.copy()
+    for row in range(out.shape[0]):
+        total = np.sum(out[row, :])
+        if total != 0:
+            out[row, :] /= total
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # vectorised equivalents (same arithmetic per pair as the loops above, batched) -- used by
 # the parity tests at sizes the Python loops cannot reach.  Each is checked against the
 # loop version in tests/test_oracle_pinned.py.

@@ -607,3 +607,30 @@ def test_get_distance_between_picks_tensor_path_for_large_inputs(S):
     d32 = S.getDistanceBetween(X.astype(np.float32), X.astype(np.float32), S.SOAPdistanceNormalized)
     assert d32.dtype == np.float32
     assert_distance_parity(d32, O.getDistanceBetween_batched(X.astype(np.float32).astype(np.float64), X.astype(np.float32).astype(np.float64), O.KIND_NORMALIZED, 1), "f32")
+
+
+# ------------------------------------------------------------------ transitions (row f4): integer, bit-exact
+def test_transition_matrix_matches_golden_and_oracle(S, golden):
+    g = golden("transitions")
+    refs = g["refs"]
+    data = S.SOAPclassification(np.zeros(refs.shape), refs, ["a", "b", "c", "d", "e"])
+    for stride, window in ((1, None), (1, 5), (3, 3), (2, 7), (1, 59), (1, 60)):
+        tag = f"s{stride}_w{window}"
+        tm = S.transitionMatrixFromSOAPClassification(data, stride, window)
+        assert tm.dtype == np.float64
+        assert_array_equal(tm, g["tm_" + tag])
+        assert_array_equal(S.transitionMatrixFromSOAPClassificationNormalized(data, stride, window), g["tmn_" + tag])
+    with pytest.raises(ValueError, match="the window must be bigger than the stride"):
+        S.transitionMatrixFromSOAPClassification(data, 3, 2)
+    with pytest.raises(ValueError, match="stride and window must be smaller"):
+        S.transitionMatrixFromSOAPClassification(data, 1, 61)
+    # many classes (global-atomic path) and a large random classification against the oracle
+    rng = np.random.default_rng(1)
+    big = rng.integers(0, 120, size=(300, 2000))
+    bd = S.SOAPclassification(np.zeros(big.shape), big, [str(i) for i in range(120)])
+    assert_array_equal(S.transitionMatrixFromSOAPClassification(bd, 2, 4), O.transitionMatrixFromSOAPClassification(big, 120, 2, 4))
+    small = rng.integers(0, 7, size=(1000, 3000))
+    sd = S.SOAPclassification(np.zeros(small.shape), small, list("abcdefg"))
+    tm = S.transitionMatrixFromSOAPClassification(sd)
+    assert_array_equal(tm, O.transitionMatrixFromSOAPClassification(small, 7))
+    assert tm.sum() == 999 * 3000
