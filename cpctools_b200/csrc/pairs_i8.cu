@@ -25,6 +25,8 @@
 
 #include <stdlib.h>
 
+#include <vector>
+
 namespace soapb {
 
 constexpr int kI8BM = 128;
@@ -125,12 +127,13 @@ __device__ __forceinline__ void tile_coords_i8(long long t, int tiles_m, int til
   tn = first + (int)(r % width);
 }
 
-template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, typename OutT>
+template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, bool SYM, typename OutT>
 __global__ void __launch_bounds__(kI8Threads, 1)
     pairs_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     OutT *__restrict__ out, const double *__restrict__ sa, const double *__restrict__ sb,
                     const double *__restrict__ uu, const double *__restrict__ vv, long long M, long long N, int KB,
-                    long long ldo, int kind, int power, int tiles_m, int tiles_n, int debug_flags) {
+                    long long ldo, int kind, int power, int tiles_m, int tiles_n, int debug_flags,
+                    const int2 *__restrict__ tile_list, long long n_listed) {
   constexpr int BM = kI8BM;
   constexpr int A_PLANE = BM * BKB, B_PLANE = BN * BKB;
   constexpr int STAGE_BYTES = ND * (A_PLANE + B_PLANE);
@@ -150,7 +153,19 @@ __global__ void __launch_bounds__(kI8Threads, 1)
   double *col_rn = reinterpret_cast<double *>(col_exp + kI8EpiWarps * BN);            // [kI8EpiWarps][BN], cosine kinds only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long tiles = (long long)tiles_m * tiles_n;
+  // symmetric mode (data is spectra): only tiles that reach the upper triangle are listed, and every
+  // computed value is also written to its mirrored position
+  constexpr bool symmetric = SYM;
+  const long long tiles = symmetric ? n_listed : (long long)tiles_m * tiles_n;
+  auto coords = [&](long long t, int &tm, int &tn) {
+    if (symmetric) {
+      const int2 c = tile_list[t];
+      tm = c.x;
+      tn = c.y;
+    } else {
+      tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -180,7 +195,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
       uint32_t ph = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         int tm, tn;
-        tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
+        coords(t, tm, tn);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait_guard(&empty[s], ph ^ 1);
           unsigned char *st = smem + (size_t)s * STAGE_BYTES;
@@ -244,7 +259,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
     int it = 0;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       int tm, tn;
-      tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
+      coords(t, tm, tn);
       const int as = it % ACC;
       if constexpr (FAST) {
         // SOAPdistanceNormalized (distances.py:83) with a lean, kind-specific epilogue.  fp32: entirely in
@@ -309,6 +324,11 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                   for (int k4 = 0; k4 < 4; ++k4)
                     if (col0 + j + k4 < N) dst[j + k4] = o[k4];
                 }
+                if (symmetric) {  // out[col][row]: the 32 lanes of a warp write 32 consecutive rows
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    if (col0 + j + k4 < N) reinterpret_cast<float *>(out)[(size_t)(col0 + j + k4) * ldo + row] = o[k4];
+                }
               }
             }
           }
@@ -358,6 +378,11 @@ __global__ void __launch_bounds__(kI8Threads, 1)
 #pragma unroll
                   for (int k2 = 0; k2 < 2; ++k2)
                     if (col0 + j + k2 < N) dst[j + k2] = o[k2];
+                }
+                if (symmetric) {
+#pragma unroll
+                  for (int k2 = 0; k2 < 2; ++k2)
+                    if (col0 + j + k2 < N) reinterpret_cast<double *>(out)[(size_t)(col0 + j + k2) * ldo + row] = o[k2];
                 }
               }
             }
@@ -454,7 +479,8 @@ __global__ void __launch_bounds__(kI8Threads, 1)
 template <int ND, int BKB>
 static size_t i8_scratch_bytes(int64_t M, int64_t N, int D) {
   const size_t Dp = align_up((size_t)D, BKB);
-  return align_up((size_t)ND * M * Dp, 1024) + align_up((size_t)ND * N * Dp, 1024) + (size_t)(M + N) * 16 + 4096;
+  const size_t tiles = ((size_t)(M + kI8BM - 1) / kI8BM) * ((size_t)(N + 31) / 32);  // upper bound on listed tiles
+  return align_up((size_t)ND * M * Dp, 1024) + align_up((size_t)ND * N * Dp, 1024) + (size_t)(M + N) * 16 + 4096 + tiles * 8;
 }
 
 template <typename InT, int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, typename OutT>
@@ -476,6 +502,7 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   double *ua = sa + M;
   double *sb = same ? sa : ua + M;
   double *ub = same ? ua : sb + N;
+  unsigned char *p_after = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<uintptr_t>((same ? ua + M : ub + N)), 16));
   ozaki_split_kernel<InT, ND><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(A, pa, sa, ua, M, D, Dp);
   int rc = check_launch("ozaki_split_kernel");
   if (rc) return rc;
@@ -488,18 +515,38 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   if ((rc = make_tensor_map_2d(&map_a, pa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * M, Dp, BKB, kI8BM, swz))) return rc;
   if ((rc = make_tensor_map_2d(&map_b, pb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * N, Dp, BKB, BN, swz))) return rc;
   const int tiles_m = (int)((M + kI8BM - 1) / kI8BM), tiles_n = (int)((N + BN - 1) / BN);
-  const long long tiles = (long long)tiles_m * tiles_n;
+  long long tiles = (long long)tiles_m * tiles_n;
+  // data is spectra: d(i,j) == d(j,i) bit for bit (exact integer sums, commutative scaling), so only
+  // the tiles that contain some j >= i are computed and every value is stored twice
+  const int2 *tile_list = nullptr;
+  long long n_listed = 0;
+  if (FAST && same && getenv("SOAP_I8_NO_SYMMETRY") == nullptr) {
+    std::vector<int2> host_list;
+    host_list.reserve((size_t)tiles / 2 + tiles_m + 16);
+    // panels of 6 tile columns walked row by row (L2 reuse), restricted to the upper triangle
+    for (int first = 0; first < tiles_n; first += 6)
+      for (int tm = 0; tm < tiles_m; ++tm)
+        for (int tn = first; tn < first + 6 && tn < tiles_n; ++tn)
+          if ((long long)(tn + 1) * BN > (long long)tm * kI8BM) host_list.push_back(make_int2(tm, tn));
+    n_listed = (long long)host_list.size();
+    int2 *dev_list = reinterpret_cast<int2 *>(p_after);
+    SOAP_CUDA(cudaMemcpyAsync(dev_list, host_list.data(), host_list.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    SOAP_CUDA(cudaStreamSynchronize(s));  // the host vector dies with this scope
+    tile_list = dev_list;
+    tiles = n_listed;
+  }
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   // the reciprocal-norm staging only exists for the cosine kinds (it would not fit beside 4 stages)
   const size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)kI8EpiWarps * BN * 4 +
                       ((FAST && kind != SOAP_KIND_NORMALIZED) ? (size_t)kI8EpiWarps * BN * 8 : 0);
   SOAP_REQUIRE(SMEM <= (size_t)max_smem_optin(), "soap_pairs: internal: tile configuration exceeds shared memory");
-  auto kern = pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, OutT>;
+  auto kern = tile_list ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, FAST, OutT>
+                        : pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, false, OutT>;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   ProfScope prof(SOAP_PROF_PAIRS, s);
   const char *dbg = getenv("SOAP_I8_DEBUG");  // experiments: 1 = skip the epilogue, 2 = one MMA per K block
   kern<<<grid, kI8Threads, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n,
-                                      dbg ? atoi(dbg) : 0);
+                                      dbg ? atoi(dbg) : 0, tile_list, n_listed);
   return check_launch("pairs_i8_kernel");
 }
 
