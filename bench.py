@@ -407,7 +407,28 @@ def run_allpairs(args, torch, dist, _lib, rank, world):
             "checksum_sample": float(chk.item()),
         }
         out["rows_per_gpu"] = rows.stop - rows.start
-        del block, X
+        del block
+        torch.cuda.empty_cache()
+        # the public all-pairs call getDistanceBetween(S, S, f) on one GPU: data is spectra, so only the
+        # upper-triangular tiles are computed and mirrored (n_sym^2 ordered pairs delivered)
+        n_sym = min(args.allpairs_symmetric, n_total)
+        if n_sym >= 1024:
+            Xs = X[:n_sym].contiguous()
+            full = torch.empty((n_sym, n_sym), dtype=dt, device="cuda")
+            sym = lambda: pairs_device(Xs, Xs, _lib.KIND_NORMALIZED, 1, path=_lib.PAIRS_TENSOR, out=full)
+            sym()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                sym()
+            e1.record()
+            torch.cuda.synchronize()
+            sms = e0.elapsed_time(e1) / reps
+            out[name]["symmetric"] = {"vectors": n_sym, "ms": sms, "pairs_per_s": n_sym * n_sym / (sms * 1e-3),
+                                      "equiv_tflops": 2.0 * n_sym * n_sym * dim / (sms * 1e-3) / 1e12,
+                                      "symmetric_max_asymmetry": float((full[:2048, :2048] - full[:2048, :2048].T).abs().max().item())}
+            del full, Xs
+        del X
         torch.cuda.empty_cache()
     return out
 
@@ -433,6 +454,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-allpairs", action="store_true")
     ap.add_argument("--allpairs-vectors", type=int, default=200000)
+    ap.add_argument("--allpairs-symmetric", type=int, default=50000, help="vectors of the single-GPU symmetric all-pairs call")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

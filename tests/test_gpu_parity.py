@@ -597,6 +597,25 @@ def test_pairs_tensor_many_tiles_persistent(S):
     assert np.abs(tf32**2 - want32**2).max() <= 5.0e-5
 
 
+@pytest.mark.parametrize("n", [1000, 1337])
+def test_symmetric_all_pairs_every_kind(S, n):
+    """data is spectra: upper-triangular tiles + mirrored stores; ragged sizes, all three kinds, both dtypes."""
+    rng = np.random.default_rng(n)
+    X = rng.random((n, 200))
+    X[5] *= 3.0e3
+    X[9, ::3] *= -1.0
+    Xn = O.normalizeArray(X)
+    for name, (fn, kind, power) in _kinds(S).items():
+        src = Xn if name == "normalized" else X
+        want = O.getDistanceBetween_batched(src, src, kind, power)
+        got = S.getDistanceBetween(src, src, fn)
+        assert_distance_parity(got, want, "f64", what=f"sym {name}")
+        assert_array_equal(got, got.T)
+        s32 = src.astype(np.float32)
+        got32 = S.getDistanceBetween(s32, s32, fn)
+        assert_distance_parity(got32, O.getDistanceBetween_batched(s32.astype(np.float64), s32.astype(np.float64), kind, power), "f32", what=f"sym32 {name}")
+
+
 def test_get_distance_between_picks_tensor_path_for_large_inputs(S):
     """the public all-pairs call (numpy in, numpy out) on a matrix large enough for the tensor path."""
     rng = np.random.default_rng(11)
