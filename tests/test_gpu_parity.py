@@ -653,3 +653,38 @@ def test_transition_matrix_matches_golden_and_oracle(S, golden):
     tm = S.transitionMatrixFromSOAPClassification(sd)
     assert_array_equal(tm, O.transitionMatrixFromSOAPClassification(small, 7))
     assert tm.sum() == 999 * 3000
+
+
+# ------------------------------------------------------------------ randomised shapes (seeded fuzz)
+def test_fuzz_random_shapes_against_oracle(S):
+    """40 seeded random cases over odd/even dimensions, tiny and ragged frame / atom counts, one to
+    four windows, both dtypes, with and without expansion: the time-lag kernel (both staging paths),
+    the expansion kernel and the SIMT pair kernel against the oracle."""
+    rng = np.random.default_rng(20261020)
+    for case in range(40):
+        nmax, lmax = int(rng.integers(1, 7)), int(rng.integers(0, 6))
+        ns = int(rng.integers(1, 4))
+        sp = [None, ["H", "O"], ["H", "C", "O"]][ns - 1]
+        if sp is None:
+            kw, dc = {}, (lmax + 1) * nmax * (nmax + 1) // 2
+        else:
+            attrs, dc = dscribe_attrs(lmax, nmax, sp)
+            kw = dict(atomTypes=sp, atomicSlices=_slices_from_attrs(attrs))
+        F, A = int(rng.integers(2, 90)), int(rng.integers(1, 40))
+        dtype = [np.float64, np.float32][case % 2]
+        path = "f64" if dtype == np.float64 else "f32"
+        raw = synthetic_soap((F, A, dc), seed=case, kind="W" if case % 3 else "U", dtype=dtype)
+        want_full = O.fillSOAPVectorFromdscribe(raw, lmax, nmax, **kw)
+        assert_array_equal(S.fillSOAPVectorFromdscribe(raw, lmax, nmax, **kw), want_full)
+        Xn = O.normalizeArray(want_full.astype(np.float64))
+        assert_allclose(S.fillAndNormalize(raw, lmax, nmax, **kw), O.normalizeArray(want_full), rtol=1e-12 if dtype == np.float64 else 2e-6, atol=0)
+        nw = int(rng.integers(1, 5))
+        windows = sorted(set(int(w) for w in rng.integers(1, F, size=nw)))
+        got = S.timeSOAPfromCompressed(raw, lmax, nmax, windows=windows, returnDiff=False, **kw)
+        for w, t in zip(windows, got):
+            assert_distance_parity(t, O.timeSOAP_batched(Xn, window=w, returnDiff=False), path, what=f"case {case} w{w}")
+        M, K = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        a, b = Xn.reshape(-1, Xn.shape[-1])[:M].astype(dtype), Xn.reshape(-1, Xn.shape[-1])[-K:].astype(dtype)
+        gotm = S.getDistanceBetween(a, b, S.SOAPdistanceNormalized)
+        assert gotm.dtype == dtype
+        assert_distance_parity(gotm, O.getDistanceBetween_batched(a.astype(np.float64), b.astype(np.float64)), path, what=f"case {case} matrix")
