@@ -295,6 +295,27 @@ def run_gpu_arm(args):
            "api": "cpctools_b200.timeSOAPfromCompressed(pinned host tensor) -> host results"}
     del host
 
+    # result collective (reported beside the step, not inside it: results stay sharded by design)
+    gather = None
+    if world > 1:
+        from cpctools_b200.sharding import gather_columns
+
+        ts, _ = out
+        full = [gather_columns(t, total_atoms) for t in ts]  # warm-up (NCCL communicator, buffers)
+        del full
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = [gather_columns(t, total_atoms) for t in ts]
+        g1.record()
+        torch.cuda.synchronize()
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        nbytes = sum(int(f.numel()) * 8 for f in full)
+        gather = {"collective": "NCCL all_gather of the t[F-w, A/G] slabs (every rank ends with t[F-w, A])",
+                  "bytes_per_rank_out": nbytes, "ms": float(gms.item()), "GBps_per_rank": nbytes / float(gms.item()) / 1e6}
+        del full
+
     # single-window calls on the same tile (what one reference call timeSOAP(window=w) costs)
     single = {}
     for w in (1, 50):
@@ -341,7 +362,7 @@ def run_gpu_arm(args):
                        "pairs_per_step": pairs_step, "l2": "inputs (>= 100 GB per GPU) far larger than the 126 MB L2",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "allpairs": allpairs,
+            "cpu_baseline": cpu_baseline, "allpairs": allpairs, "result_gather": gather,
         }
         print(json.dumps(line))
     if world > 1:
