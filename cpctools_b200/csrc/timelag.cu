@@ -21,23 +21,23 @@
 // frame; the 8 warps split the elements and are summed once per 32-frame block.
 // Partial sums (uu, uv_w) go to scratch[a][p][q][f]; a small finalize kernel sums the pieces in
 // fixed order (deterministic), applies the distance epilogue and writes t_w[f-w][a].
-#include "common.cuh"
+#include "tc05.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace soapb {
 
-constexpr int kTlWarps = 12;                     // consumer warps (3 per SM sub-partition)
-constexpr int kTlThreads = (kTlWarps + 2) * 32;  // + producer warp + reducer warp
-constexpr int kBlk = 32;  // frames per block == lanes per warp
+constexpr int kBlk = 32;     // frames per block == lanes per warp
+constexpr int kTlWarps = 8;  // consumer warps (two per SM sub-partition)
 
 struct TimelagPlan {
-  int unit_elems, n_units, split, upp, stride, R, ahead, Q, max_lag;
+  int unit_elems, n_units, split, upp, stride, R, ahead, Q, max_lag, cw, mbuf;
   size_t smem;
 };
 
-static size_t tl_smem_bytes(int R, int stride, int upp, int Q) {
-  return (size_t)R * stride + (size_t)upp * 16 + (size_t)kTlWarps * Q * 32 * 8 + (size_t)(2 * (R / kBlk) + 2) * 8 + 64;
+static size_t tl_smem_bytes(int R, int stride, int upp, int Q, int cw, int mbuf) {
+  return (size_t)R * stride + (size_t)mbuf * upp * 16 + (size_t)cw * Q * 32 * 8 + (size_t)(2 * (R / kBlk) + 2) * 8 + 64;
 }
 
 static int env_int(const char *name, int dflt) {
@@ -45,7 +45,7 @@ static int env_int(const char *name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-static bool make_plan(int D, int elem_size, const int *windows, int nw, TimelagPlan &pl) {
+static bool make_plan(int64_t F, int D, int elem_size, const int *windows, int nw, TimelagPlan &pl) {
   pl.unit_elems = 16 / elem_size;
   pl.n_units = (D + pl.unit_elems - 1) / pl.unit_elems;
   pl.Q = 1 + nw;
@@ -54,15 +54,24 @@ static bool make_plan(int D, int elem_size, const int *windows, int nw, TimelagP
   const size_t budget = (size_t)max_smem_optin() - 1024;
   const int force_split = env_int("SOAP_TL_SPLIT", 0);    // tuning knobs (benchmarks only)
   const int force_ahead = env_int("SOAP_TL_AHEAD", 0);
+  pl.cw = env_int("SOAP_TL_WARPS", kTlWarps);
   for (int split = force_split > 0 ? force_split : 1; split <= pl.n_units; ++split) {
-    const int upp = (pl.n_units + split - 1) / split;
+    // units per piece: odd (ring slots 16*odd bytes apart -> conflict-free 128-bit LDS) and <= 127
+    // (one tensor-map box row holds at most 256 8-byte elements)
+    const int upp = ((pl.n_units + split - 1) / split) | 1;
+    if (upp > 127) continue;
     const int real_split = (pl.n_units + upp - 1) / upp;  // no empty pieces
-    const int stride = 16 * (upp | 1);
+    const int stride = 16 * upp;
     for (int ahead = force_ahead > 0 ? force_ahead : 3; ahead >= 1; --ahead) {
       // ring = blocks still needed as lag partners + the block being consumed + `ahead` in flight
       const int R = kBlk * ((pl.max_lag + kBlk - 1) / kBlk + 1 + ahead);
-      const size_t smem = tl_smem_bytes(R, stride, upp, pl.Q);
+      // multiplicity buffers: item k's may only be overwritten once item k - mbuf is consumed, which the
+      // producer knows (from the ring's own hand-shake) when mbuf - 1 items are at least `ahead` blocks
+      const int64_t nblk = (F + kBlk - 1) / kBlk;
+      const int mbuf = nblk >= ahead ? 2 : 4;
+      const size_t smem = tl_smem_bytes(R, stride, upp, pl.Q, pl.cw, mbuf);
       if (smem <= budget) {
+        pl.mbuf = mbuf;
         pl.split = real_split;
         pl.upp = upp;
         pl.stride = stride;
@@ -77,11 +86,14 @@ static bool make_plan(int D, int elem_size, const int *windows, int nw, TimelagP
   return false;
 }
 
-__device__ __forceinline__ void cp_async_elem(uint32_t dst, const void *src, int bytes) {
-  if (bytes == 8)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+// one element global -> shared; `valid == false` writes zeros instead (src-size 0)
+template <size_t BYTES>
+__device__ __forceinline__ void cp_async_elem(uint32_t dst, const void *src, bool valid) {
+  const uint32_t n = valid ? (uint32_t)BYTES : 0u;
+  if constexpr (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
   else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -90,13 +102,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
 // U units (16 bytes each) of the lane's frame against the NW lagged frames.  All loads are issued
 // before the first use so that one warp keeps U*(NW+2) shared-memory requests in flight.
 // fp64: exact products accumulated by DFMA, separate chains for the two halves of a unit.
-template <int NW, int U, bool EUCLID>
+template <int NW, int U, bool EUCLID, bool HM>
 __device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
                                                 uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
   double2 m[U], x[U], y[NW][U];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
-    m[j] = lds_d2(m_addr + off + j * ustep);
+    m[j] = HM ? lds_d2(m_addr + off + j * ustep) : make_double2(1.0, 1.0);
     x[j] = lds_d2(x_addr + off + j * ustep);
 #pragma unroll
     for (int k = 0; k < NW; ++k) y[k][j] = lds_d2(y_addr[k] + off + j * ustep);
@@ -122,13 +134,13 @@ __device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr
 
 // fp32 data: products and a chain of 4*U terms in fp32, chain sums promoted to double (one
 // conversion per 4*U products; the fp32 rounding is bounded to one short chain).
-template <int NW, int U, bool EUCLID>
+template <int NW, int U, bool EUCLID, bool HM>
 __device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
                                                 uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
   float4 m[U], x[U], y[NW][U];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
-    m[j] = lds_f4(m_addr + off + j * ustep);
+    m[j] = HM ? lds_f4(m_addr + off + j * ustep) : make_float4(1.f, 1.f, 1.f, 1.f);
     x[j] = lds_f4(x_addr + off + j * ustep);
 #pragma unroll
     for (int k = 0; k < NW; ++k) y[k][j] = lds_f4(y_addr[k] + off + j * ustep);
@@ -166,154 +178,210 @@ __device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr
   }
 }
 
-template <typename T, int NW, int U, bool EUCLID>
+template <typename T, int NW, int U, bool EUCLID, bool HM>
 __device__ __forceinline__ void accum_units(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
                                             uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
   if constexpr (sizeof(T) == 8)
-    accum_units_f64<NW, U, EUCLID>(m_addr, x_addr, y_addr, off, ustep, acc);
+    accum_units_f64<NW, U, EUCLID, HM>(m_addr, x_addr, y_addr, off, ustep, acc);
   else
-    accum_units_f32<NW, U, EUCLID>(m_addr, x_addr, y_addr, off, ustep, acc);
+    accum_units_f32<NW, U, EUCLID, HM>(m_addr, x_addr, y_addr, off, ustep, acc);
 }
 
-// Warp roles: warps 0..11 consume (lane = frame), warp 12 produces (TMA / cp.async), warp 13 reduces
+// Warp roles: warps 0..CW-1 consume (lane = frame), warp CW produces (TMA / cp.async), warp CW+1 reduces
 // the consumers' partial sums of a block and writes them to scratch.  All hand-offs are
 // mbarriers; there is no __syncthreads after the prologue, so no warp ever convoys behind another.
 //   full[s]      producer -> consumers   block in ring slot-group s has landed
 //   empty[s]     consumers -> producer   block s consumed as "current" frames (one arrival per warp)
 //   red_full     consumers -> reducer    partial sums of a block are in red (one arrival per warp)
 //   red_empty    reducer -> consumers    red may be overwritten
-template <typename T, int NW, bool EUCLID>
-__global__ void __launch_bounds__(kTlThreads, 1)
+// The kernel is PERSISTENT: a CTA walks the work items i = blockIdx.x, + gridDim.x, ... (item = atom a,
+// piece p) as one continuous stream of 32-frame blocks, so the producer is already fetching the next
+// item's first frames while the consumers finish the current one (no per-item pipeline fill).
+struct TlItem {
+  long long a;
+  int p, e0, pe, punits;
+};
+
+template <int UE>
+__device__ __forceinline__ TlItem tl_item(long long i, int split, int upp, int D) {
+  TlItem it;
+  it.a = i / split;
+  it.p = (int)(i - it.a * split);
+  it.e0 = it.p * upp * UE;
+  it.pe = min(D - it.e0, upp * UE);  // elements of this piece (> 0)
+  it.punits = (it.pe + UE - 1) / UE;
+  return it;
+}
+
+template <typename T, int NW, bool EUCLID, bool HAS_MULT, int CW, int UB>
+__global__ void __launch_bounds__((CW + 2) * 32, 1)
     timelag_kernel(const T *__restrict__ X, const T *__restrict__ mult, double *__restrict__ scratch,
                    long long F, long long A, int D, int split, int upp, int stride, int R, int lag_blocks,
-                   int4 win4, int bulk_ok) {
+                   int mbuf, int4 win4, int bulk_ok, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int UE = 16 / (int)sizeof(T);
   constexpr int Q = NW + 1;
+  constexpr int kTlThreads = (CW + 2) * 32;  // consumers + producer warp + reducer warp
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int win[4] = {win4.x, win4.y, win4.z, win4.w};
   const int nslots = R / kBlk;
 
   unsigned char *ring = smem_raw;
-  unsigned char *msm = ring + (size_t)R * stride;
-  double *red = reinterpret_cast<double *>(msm + (size_t)upp * 16);      // [kTlWarps][Q][32]
-  uint64_t *full = reinterpret_cast<uint64_t *>(red + kTlWarps * Q * 32);  // [nslots]
+  unsigned char *msm = ring + (size_t)R * stride;                          // [mbuf][upp] units
+  double *red = reinterpret_cast<double *>(msm + (size_t)mbuf * upp * 16);  // [CW][Q][32]
+  uint64_t *full = reinterpret_cast<uint64_t *>(red + CW * Q * 32);  // [nslots]
   uint64_t *empty = full + nslots;                                        // [nslots]
   uint64_t *red_full = empty + nslots;                                    // [1]
   uint64_t *red_empty = red_full + 1;                                     // [1]
 
-  const long long a = blockIdx.x / split;
-  const int p = (int)(blockIdx.x - a * split);
-  const int e0 = p * upp * UE;
-  const int pe = min(D - e0, upp * UE);  // elements of this piece (> 0)
-  const int punits = (pe + UE - 1) / UE;
-  const uint32_t pbytes = (uint32_t)pe * sizeof(T);
+  const long long n_items = A * split;
+  const long long first = blockIdx.x;
+  const int n_my = first < n_items ? (int)((n_items - first + gridDim.x - 1) / gridDim.x) : 0;
   const int nblk = (int)((F + kBlk - 1) / kBlk);
 
-  // prologue (all warps): multiplicities of this piece, zero padded; ring zeroed when rows are not
-  // 16-byte multiples (the tail unit is then partial and its padding must read as zero)
-  for (int i = tid; i < upp * UE; i += kTlThreads)
-    reinterpret_cast<T *>(msm)[i] = (i < pe) ? (mult ? mult[e0 + i] : (T)1) : (T)0;
-  if (!bulk_ok) {
-    const int n16 = (int)(((size_t)R * stride) / 16);
+  // prologue (all warps): the ring is zeroed when rows are not 16-byte multiples (the tail unit of a
+  // row is then partial and its padding must read as zero)
+  if (!(bulk_ok & 1)) {
+    const int n16 = (int)(((size_t)R * stride + (size_t)mbuf * upp * 16) / 16);
     for (int i = tid; i < n16; i += kTlThreads) reinterpret_cast<int4 *>(ring)[i] = make_int4(0, 0, 0, 0);
   }
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
-      mbar_init(&full[s], bulk_ok ? 1 : 32);
-      mbar_init(&empty[s], kTlWarps);
+      mbar_init(&full[s], (bulk_ok & 1) ? 1 : 32);
+      mbar_init(&empty[s], CW);
     }
-    mbar_init(red_full, kTlWarps);
+    mbar_init(red_full, CW);
     mbar_init(red_empty, 1);
     fence_mbar_init();
   }
   __syncthreads();
 
-  if (warp == kTlWarps) {
+  if (warp == CW) {
     // ===== producer ==========================================================================
     const size_t fstride = (size_t)A * D;  // elements between consecutive frames
-    const T *xa = X + (size_t)a * D + e0;
-    const uint32_t ring_addr = smem_u32(ring);
-    for (int c = 0; c < nblk; ++c) {
-      // loading block c overwrites the frames of block c - nslots, last needed (as lag partners)
-      // by block j = c - nslots + lag_blocks: wait until the consumers are done with block j
-      const int j = c - nslots + lag_blocks;
-      if (j >= 0) mbar_wait(&empty[j % nslots], (uint32_t)((j / nslots) & 1));
-      const long long f0 = (long long)c * kBlk;
-      const int nf = (int)min((long long)kBlk, F - f0);
-      const int s = c % nslots;
-      if (bulk_ok) {
-        if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nf * pbytes);
-        __syncwarp();
-        if (lane < nf)
-          bulk_g2s(ring + (size_t)(s * kBlk + lane) * stride, xa + (size_t)(f0 + lane) * fstride, pbytes, &full[s]);
-      } else {
-        for (int fr = 0; fr < nf; ++fr) {
-          const T *src = xa + (size_t)(f0 + fr) * fstride;
-          const uint32_t dst = ring_addr + (uint32_t)(s * kBlk + fr) * stride;
-          for (int e = lane; e < pe; e += 32) cp_async_elem(dst + e * (uint32_t)sizeof(T), src + e, (int)sizeof(T));
+    const uint32_t ring_addr = smem_u32(ring), msm_addr = smem_u32(msm);
+    // loading block g overwrites the frames of block g - nslots, last needed (as lag partners) by
+    // block j = g - back: wait until the consumers are done with block j
+    const int back = nslots - lag_blocks;
+    int s = 0, js = 0, jph = 0, g = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const TlItem it = tl_item<UE>(first + (long long)k * gridDim.x, split, upp, D);
+      const T *xa = X + (size_t)it.a * D + it.e0;
+      const int mslot = k & (mbuf - 1);
+      for (int b = 0; b < nblk; ++b, ++g) {
+        if (g >= back) {
+          mbar_wait(&empty[js], (uint32_t)jph);
+          if (++js == nslots) js = 0, jph ^= 1;
         }
-        cp_async_arrive_noinc(&full[s]);  // every lane: arrives once its own copies have landed
+        const long long f0 = (long long)b * kBlk;
+        if (bulk_ok & 2) {  // diagnostic: no copies
+          if (lane == 0) mbar_arrive(&full[s]);
+        } else if (bulk_ok & 1) {
+          // ONE tensor-map box = 32 frames x this piece (rows beyond F and columns beyond the tensor are
+          // zero-filled and still counted in the transaction bytes); the item's multiplicities ride on
+          // the barrier of its first block
+          if (lane == 0) {
+            const uint32_t mbytes = (HAS_MULT && b == 0) ? (uint32_t)it.pe * (uint32_t)sizeof(T) : 0u;
+            mbar_expect_tx(&full[s], (uint32_t)kBlk * (uint32_t)stride + mbytes);
+            tma_load_2d(ring + (size_t)s * kBlk * stride, &tmap, (int)(((size_t)it.a * D + it.e0) * sizeof(T) / 8),
+                        (int)f0, &full[s]);
+            if (mbytes) bulk_g2s(msm + (size_t)mslot * upp * 16, mult + it.e0, mbytes, &full[s]);
+          }
+        } else {
+          const int nf = (int)min((long long)kBlk, F - f0);
+          const int padded = it.punits * UE;  // the tail of a partial last unit is written as zeros
+          for (int fr = 0; fr < nf; ++fr) {
+            const T *src = xa + (size_t)(f0 + fr) * fstride;
+            const uint32_t dst = ring_addr + (uint32_t)(s * kBlk + fr) * stride;
+            for (int e = lane; e < padded; e += 32)
+              cp_async_elem<sizeof(T)>(dst + e * (uint32_t)sizeof(T), src + min(e, it.pe - 1), e < it.pe);
+          }
+          if (HAS_MULT && b == 0) {
+            const uint32_t dst = msm_addr + (uint32_t)mslot * upp * 16;
+            for (int e = lane; e < padded; e += 32)
+              cp_async_elem<sizeof(T)>(dst + e * (uint32_t)sizeof(T), mult + it.e0 + min(e, it.pe - 1), e < it.pe);
+          }
+          cp_async_arrive_noinc(&full[s]);  // every lane: arrives once its own copies have landed
+        }
+        if (++s == nslots) s = 0;
       }
     }
-  } else if (warp == kTlWarps + 1) {
+  } else if (warp == CW + 1) {
     // ===== reducer ===========================================================================
-    double *srow = scratch + ((size_t)a * split + p) * Q * (size_t)F;
-    for (int b = 0; b < nblk; ++b) {
-      mbar_wait(red_full, (uint32_t)(b & 1));
-      const double *r = red;
-      const long long fl = (long long)b * kBlk + lane;
+    int g = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const TlItem it = tl_item<UE>(first + (long long)k * gridDim.x, split, upp, D);
+      double *srow = scratch + ((size_t)it.a * split + it.p) * Q * (size_t)F;
+      for (int b = 0; b < nblk; ++b, ++g) {
+        mbar_wait(red_full, (uint32_t)(g & 1));
+        const long long fl = (long long)b * kBlk + lane;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        double s = 0.0;
+        for (int q = 0; q < Q; ++q) {
+          double sum = 0.0;
 #pragma unroll
-        for (int w = 0; w < kTlWarps; ++w) s += r[(w * Q + q) * 32 + lane];
-        if (fl < F) srow[(size_t)q * F + fl] = s;
+          for (int w = 0; w < CW; ++w) sum += red[(w * Q + q) * 32 + lane];
+          if (fl < F) srow[(size_t)q * F + fl] = sum;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(red_empty);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(red_empty);
     }
   } else {
     // ===== consumers: lane <-> frame ============================================================
-    const uint32_t ring_addr = smem_u32(ring), m_addr = smem_u32(msm);
-    const uint32_t ustep = 16u * kTlWarps;  // this warp's units are u = warp, warp + kTlWarps, ...
+    const uint32_t ring_addr = smem_u32(ring), msm_addr = smem_u32(msm);
+    const uint32_t ustep = 16u * CW;  // this warp's units are u = warp, warp + CW, ...
     const uint32_t off0 = 16u * warp;
-    const int my_units = punits > warp ? (punits - warp + kTlWarps - 1) / kTlWarps : 0;
     int wmod[NW];
 #pragma unroll
     for (int k = 0; k < NW; ++k) wmod[k] = win[k] % R;
-    for (int b = 0; b < nblk; ++b) {
-      const int s = b % nslots;
-      const int slot = s * kBlk + lane;  // ring slot of this lane's frame (R is a multiple of 32)
-      const uint32_t x_addr = ring_addr + (uint32_t)slot * stride;
-      uint32_t y_addr[NW];
+    int s = 0, ph = 0, g = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const TlItem it = tl_item<UE>(first + (long long)k * gridDim.x, split, upp, D);
+      const int my_units = it.punits > warp ? (it.punits - warp + CW - 1) / CW : 0;
+      const uint32_t m_addr = msm_addr + (uint32_t)(k & (mbuf - 1)) * upp * 16;
+      for (int b = 0; b < nblk; ++b, ++g) {
+        const int slot = s * kBlk + lane;  // ring slot of this lane's frame (R is a multiple of 32)
+        const uint32_t x_addr = ring_addr + (uint32_t)slot * stride;
+        uint32_t y_addr[NW];
 #pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        int ys = slot - wmod[k];
-        if (ys < 0) ys += R;
-        y_addr[k] = ring_addr + (uint32_t)ys * stride;  // frames f < w read stale data: result unused
-      }
-      double acc[2 * Q];
+        for (int q = 0; q < NW; ++q) {
+          int ys = slot - wmod[q];
+          if (ys < 0) ys += R;
+          y_addr[q] = ring_addr + (uint32_t)ys * stride;  // frames f < w read stale data: result unused
+        }
+        double acc[2 * Q];
 #pragma unroll
-      for (int q = 0; q < 2 * Q; ++q) acc[q] = 0.0;
-      mbar_wait(&full[s], (uint32_t)((b / nslots) & 1));
-      int n = 0;
-      for (; n + 4 <= my_units; n += 4)
-        accum_units<T, NW, 4, EUCLID>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
-      if (n + 2 <= my_units) {
-        accum_units<T, NW, 2, EUCLID>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
-        n += 2;
-      }
-      if (n < my_units) accum_units<T, NW, 1, EUCLID>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
-      // hand the partial sums to the reducer (it is ~10x faster than a block: this wait is free)
-      if (b >= 1) mbar_wait(red_empty, (uint32_t)((b - 1) & 1));
-      double *r = red + (size_t)warp * Q * 32;
+        for (int q = 0; q < 2 * Q; ++q) acc[q] = 0.0;
+        mbar_wait(&full[s], (uint32_t)ph);
+        int n = 0;
+        if (bulk_ok & 4) n = my_units;  // diagnostic: no accumulation
+        for (; n + UB <= my_units; n += UB)
+          accum_units<T, NW, UB, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+        if constexpr (UB > 4) {
+          if (n + 4 <= my_units) {
+            accum_units<T, NW, 4, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+            n += 4;
+          }
+        }
+        if constexpr (UB > 2) {
+          if (n + 2 <= my_units) {
+            accum_units<T, NW, 2, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+            n += 2;
+          }
+        }
+        if (n < my_units)
+          accum_units<T, NW, 1, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+        // hand the partial sums to the reducer (it is ~10x faster than a block: this wait is free)
+        if (g >= 1) mbar_wait(red_empty, (uint32_t)((g - 1) & 1));
+        double *r = red + (size_t)warp * Q * 32;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) r[q * 32 + lane] = acc[2 * q] + acc[2 * q + 1];
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(red_full);
-        mbar_arrive(&empty[s]);
+        for (int q = 0; q < Q; ++q) r[q * 32 + lane] = acc[2 * q] + acc[2 * q + 1];
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(red_full);
+          mbar_arrive(&empty[s]);
+        }
+        if (++s == nslots) s = 0, ph ^= 1;
       }
     }
   }
@@ -380,18 +448,51 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <typename T, int NW>
+template <typename T, int NW, bool HM>
 static int launch_timelag(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D,
                           const TimelagPlan &pl, const int *w, int kind, int bulk_ok, cudaStream_t s) {
   const int4 win4 = make_int4(w[0], NW > 1 ? w[1] : 0, NW > 2 ? w[2] : 0, NW > 3 ? w[3] : 0);
-  auto kern = (kind == SOAP_KIND_EUCLID) ? timelag_kernel<T, NW, true> : timelag_kernel<T, NW, false>;
+  auto kern = (kind == SOAP_KIND_EUCLID) ? timelag_kernel<T, NW, true, HM, kTlWarps, 4>
+                                         : timelag_kernel<T, NW, false, HM, kTlWarps, 4>;
+  int cw = kTlWarps;
+  if constexpr (NW == 4 && sizeof(T) == 8 && HM) {  // launch-shape experiments (scripts/tl_sweep.py)
+    if (kind != SOAP_KIND_EUCLID && pl.cw != kTlWarps) {
+      cw = pl.cw;
+#define TL_VAR(W, B) if (cw == W) kern = timelag_kernel<T, NW, false, HM, W, B>;
+      TL_VAR(4, 4) TL_VAR(6, 4) TL_VAR(10, 4) TL_VAR(12, 4)
+#undef TL_VAR
+    }
+  }
+  SOAP_REQUIRE(cw == pl.cw, "soap_timelag: SOAP_TL_WARPS=%d is only built for the 4-window f64 sweep", pl.cw);
+  const int threads = (cw + 2) * 32;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  const long long nblocks = (long long)A * pl.split;
-  SOAP_REQUIRE(nblocks < 2147483647LL, "soap_timelag: atoms x pieces = %lld exceeds the grid limit", nblocks);
+  const long long n_items = (long long)A * pl.split;
+  SOAP_REQUIRE(n_items < 2147483647LL, "soap_timelag: atoms x pieces = %lld exceeds the item limit", n_items);
+  // persistent grid: as many CTAs as fit on the device at once (one per SM with a full-size ring)
+  int dev = 0, sms = 0, per_sm = 0;
+  SOAP_CUDA(cudaGetDevice(&dev));
+  SOAP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SOAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, pl.smem));
+  SOAP_REQUIRE(per_sm >= 1, "soap_timelag: kernel does not fit on an SM (%zu bytes of shared memory)", pl.smem);
+  long long grid = (long long)sms * per_sm;
+  const int force_grid = env_int("SOAP_TL_GRID", 0);
+  if (force_grid > 0) grid = force_grid;
+  if (grid > n_items) grid = n_items;
+  // X viewed as a 2-D tensor [F][A*D] of 8-byte words; box = 32 frames x one piece (stride bytes)
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (bulk_ok & 1) {
+    const int64_t row_words = (int64_t)A * D * (int64_t)sizeof(T) / 8;
+    SOAP_REQUIRE(row_words < 2147483647LL, "soap_timelag: a frame of %lld bytes exceeds the tensor-map coordinate range",
+                 (long long)row_words * 8);
+    const int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, pl.stride / 8, kBlk,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
   ProfScope prof(SOAP_PROF_TIMELAG, s);
-  kern<<<(unsigned)nblocks, kTlThreads, pl.smem, s>>>(static_cast<const T *>(X), static_cast<const T *>(mult),
-                                                      scratch, (long long)F, (long long)A, D, pl.split, pl.upp,
-                                                      pl.stride, pl.R, (pl.max_lag + kBlk - 1) / kBlk, win4, bulk_ok);
+  kern<<<(unsigned)grid, threads, pl.smem, s>>>(static_cast<const T *>(X), static_cast<const T *>(mult), scratch,
+                                                (long long)F, (long long)A, D, pl.split, pl.upp, pl.stride, pl.R,
+                                                (pl.max_lag + kBlk - 1) / kBlk, pl.mbuf, win4, bulk_ok, tmap);
   return check_launch("timelag_kernel");
 }
 
@@ -423,7 +524,7 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
   if (n_frames <= 0 || n_atoms <= 0 || dim <= 0 || !windows_host || n_windows < 1 || n_windows > SOAP_MAX_WINDOWS)
     return 0;
   TimelagPlan pl;
-  if (!make_plan(dim, dtype == SOAP_F64 ? 8 : 4, windows_host, n_windows, pl)) return 0;
+  if (!make_plan(n_frames, dim, dtype == SOAP_F64 ? 8 : 4, windows_host, n_windows, pl)) return 0;
   return (size_t)n_atoms * pl.split * pl.Q * (size_t)n_frames * sizeof(double);
 }
 
@@ -438,14 +539,18 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
   if (rc) return rc;
   const int es = dtype == SOAP_F64 ? 8 : 4;
   TimelagPlan pl;
-  if (!make_plan(dim, es, windows_host, n_windows, pl))
+  if (!make_plan(n_frames, dim, es, windows_host, n_windows, pl))
     return set_error(SOAP_EUNSUPPORTED, "soap_timelag: window %d needs more shared memory than one SM has", pl.max_lag);
-  const int bulk_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (((size_t)dim * es) % 16 == 0);
+  // TMA path: 16-byte aligned base pointers and rows that are whole 16-byte units
+  int bulk_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (((size_t)dim * es) % 16 == 0) &&
+                ((reinterpret_cast<uintptr_t>(mult) & 15) == 0);
+  if (bulk_ok) bulk_ok |= env_int("SOAP_TL_DIAG", 0) & 30;
   auto s = static_cast<cudaStream_t>(stream);
   auto sc = static_cast<double *>(scratch);
 #define TL_CASE(T, NW)                                                                                          \
   case NW:                                                                                                      \
-    rc = launch_timelag<T, NW>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, s);        \
+    rc = mult ? launch_timelag<T, NW, true>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, s)  \
+              : launch_timelag<T, NW, false>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, s); \
     if (rc) return rc;                                                                                          \
     return launch_finalize<NW>(sc, t, t_offsets_host, n_frames, n_atoms, pl, windows_host, kind, power, s);
   if (dtype == SOAP_F64) {
