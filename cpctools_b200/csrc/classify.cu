@@ -13,7 +13,7 @@
 // vector and nothing else: no expanded / normalised copy of the dataset ever exists.
 // One warp per vector, 128-bit streaming loads, R' and the multiplicities in shared memory,
 // K+1 warp reductions per vector, numpy's argmin rules (first NaN, then first minimum).
-#include "common.cuh"
+#include "tc05.cuh"
 
 namespace soapb {
 
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kClsThreads, 2)
 // the distance and the arg-minimum and writes the results; tiles and partial-sum buffers are double
 // buffered and every hand-off is an mbarrier (no __syncthreads after the prologue).
 constexpr int kCtWarps = 8;
-constexpr int kCtThreads = (kCtWarps + 2) * 32;  // + TMA producer warp + finisher warp
+constexpr int kCtThreads = (kCtWarps + 3) * 32;  // + TMA producer warp + two finisher warps (alternating tiles)
 constexpr int kCtMaxK = 32;
 
 template <typename T, int KMAX>
@@ -115,18 +115,19 @@ __global__ void __launch_bounds__(kCtThreads, 1)
     classify_tiled_kernel(const T *__restrict__ X, const double *__restrict__ mult, const double *__restrict__ refw,
                           const double *__restrict__ ref_norm2, long long nvec, int D, int K, int kind, int power,
                           int normalize_x, double *__restrict__ dist_out, int *__restrict__ argmin_out,
-                          double *__restrict__ min_out, int upp, int npieces, int stride) {
+                          double *__restrict__ min_out, int upp, int npieces, int stride, int nstage,
+                          const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_ct[];
   constexpr int UE = 16 / (int)sizeof(T);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Dp = npieces * upp * UE;                   // padded dimension (multiple of the unit)
-  unsigned char *stage0 = smem_ct;                     // [2][32 slots][stride]
-  double *sm_m = reinterpret_cast<double *>(smem_ct + (size_t)2 * 32 * stride);  // [Dp]
+  unsigned char *stage0 = smem_ct;                     // [nstage][32 slots][stride]
+  double *sm_m = reinterpret_cast<double *>(smem_ct + (size_t)nstage * 32 * stride);  // [Dp]
   double *sm_r = sm_m + Dp;                            // [K][Dp]
   double *red = sm_r + (size_t)K * Dp;                 // [2][kCtWarps][K+1][32]
   const size_t red_elems = (size_t)kCtWarps * (K + 1) * 32;
-  uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * red_elems);
-  uint64_t *empty = full + 2, *red_full = full + 4, *red_empty = full + 6;
+  uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * red_elems);  // [nstage]
+  uint64_t *empty = full + nstage, *red_full = empty + nstage, *red_empty = red_full + 2;
 
   for (int i = tid; i < Dp; i += kCtThreads) sm_m[i] = i < D ? (mult ? mult[i] : 1.0) : 0.0;
   for (int i = tid; i < K * Dp; i += kCtThreads) {
@@ -134,9 +135,11 @@ __global__ void __launch_bounds__(kCtThreads, 1)
     sm_r[i] = e < D ? refw[(size_t)k * D + e] : 0.0;
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < nstage; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kCtWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&red_full[s], kCtWarps);
       mbar_init(&red_empty[s], 1);
     }
@@ -147,25 +150,27 @@ __global__ void __launch_bounds__(kCtThreads, 1)
   const long long ntiles = (nvec + 31) / 32;
   const long long my_first = blockIdx.x;
   if (warp == kCtWarps) {
-    // ===== producer: one bulk copy per vector row piece ===========================================
+    // ===== producer: ONE tensor-map box (32 vectors x one piece) per stage ==========================
+    // rows beyond nvec and columns beyond D are zero-filled and still counted in the transaction
+    int s = 0, ph = 0;
     long long it = 0;
     for (long long t = my_first; t < ntiles; t += gridDim.x) {
-      const int nv = (int)min(32LL, nvec - t * 32);
       for (int p = 0; p < npieces; ++p, ++it) {
-        const int s = (int)(it & 1);
-        if (it >= 2) mbar_wait(&empty[s], (uint32_t)(((it >> 1) - 1) & 1));
-        const int e0 = p * upp * UE;
-        const uint32_t pbytes = (uint32_t)(min(D - e0, upp * UE) * (int)sizeof(T));
-        if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)nv * pbytes);
-        __syncwarp();
-        if (lane < nv)
-          bulk_g2s(stage0 + ((size_t)s * 32 + lane) * stride, X + (size_t)(t * 32 + lane) * D + e0, pbytes, &full[s]);
+        if (it >= nstage) mbar_wait(&empty[s], (uint32_t)(ph ^ 1));
+        if (lane == 0) {
+          mbar_expect_tx(&full[s], 32u * (uint32_t)stride);
+          tma_load_2d(stage0 + (size_t)s * 32 * stride, &tmap, p * (stride / 8), (int)(t * 32), &full[s]);
+        }
+        if (++s == nstage) s = 0, ph ^= 1;
       }
     }
-  } else if (warp == kCtWarps + 1) {
-    // ===== finisher: sums of the consumers' partials -> distances, arg-minimum, results ===========
-    long long tcount = 0;
-    for (long long t = my_first; t < ntiles; t += gridDim.x, ++tcount) {
+  } else if (warp > kCtWarps) {
+    // ===== finishers: sums of the consumers' partials -> distances, arg-minimum, results ==========
+    // (the fp64 sqrt / divide chains of K distances take about as long as the consumers need for a
+    // tile: two warps take alternate tiles, each owning one of the two partial-sum buffers)
+    const int fin = warp - kCtWarps - 1;
+    long long tcount = fin;
+    for (long long t = my_first + (long long)fin * gridDim.x; t < ntiles; t += 2LL * gridDim.x, tcount += 2) {
       const int rb = (int)(tcount & 1);
       mbar_wait(&red_full[rb], (uint32_t)((tcount >> 1) & 1));
       const double *r = red + rb * red_elems;
@@ -174,18 +179,24 @@ __global__ void __launch_bounds__(kCtThreads, 1)
       for (int w = 0; w < kCtWarps; ++w) uu += r[((size_t)w * (K + 1)) * 32 + lane];
       double best_v = 0.0;
       int best_j = -1;
-      for (int k = 0; k < K; ++k) {
-        double uv = 0.0;
-        for (int w = 0; w < kCtWarps; ++w) uv += r[((size_t)w * (K + 1) + k + 1) * 32 + lane];
-        double d;
-        if (kind == SOAP_KIND_NORMALIZED) {
-          const double nu = normalize_x ? ((uu == 0.0) ? 1.0 : sqrt(uu)) : 1.0;
-          d = sqrt(fabs(2.0 - 2.0 * (uv / nu)));
-        } else {
-          d = soap_epilogue(uv, uu, ref_norm2[k], kind, power);
+      const double nu = (kind == SOAP_KIND_NORMALIZED && normalize_x) ? ((uu == 0.0) ? 1.0 : sqrt(uu)) : 1.0;
+      double d[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {  // independent chains: the compiler interleaves them
+        if (k < K) {
+          double uv = 0.0;
+#pragma unroll
+          for (int w = 0; w < kCtWarps; ++w) uv += r[((size_t)w * (K + 1) + k + 1) * 32 + lane];
+          d[k] = (kind == SOAP_KIND_NORMALIZED) ? sqrt(fabs(2.0 - 2.0 * (uv / nu)))
+                                                : soap_epilogue(uv, uu, ref_norm2[k], kind, power);
         }
-        if (v < nvec && dist_out) dist_out[(size_t)v * K + k] = d;
-        if (best_j < 0 || cls_better(d, k, best_v, best_j)) { best_v = d; best_j = k; }
+      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          if (v < nvec && dist_out) dist_out[(size_t)v * K + k] = d[k];
+          if (best_j < 0 || cls_better(d[k], k, best_v, best_j)) { best_v = d[k]; best_j = k; }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&red_empty[rb]);
@@ -197,16 +208,16 @@ __global__ void __launch_bounds__(kCtThreads, 1)
   } else {
     // ===== consumers ================================================================================
     const uint32_t st_addr = smem_u32(stage0), m_addr = smem_u32(sm_m), r_addr = smem_u32(sm_r);
-    long long it = 0, tcount = 0;
+    long long tcount = 0;
+    int s = 0, ph = 0;
     for (long long t = my_first; t < ntiles; t += gridDim.x) {
       double acc[KMAX + 1];  // statically indexed everywhere: stays in registers
 #pragma unroll
       for (int q = 0; q <= KMAX; ++q) acc[q] = 0.0;
-      for (int p = 0; p < npieces; ++p, ++it) {
-        const int s = (int)(it & 1);
+      for (int p = 0; p < npieces; ++p) {
         const int e0 = p * upp * UE;
         const int punits = (min(D - e0, upp * UE) + UE - 1) / UE;
-        mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));
+        mbar_wait(&full[s], (uint32_t)ph);
         const uint32_t xrow = st_addr + (uint32_t)((s * 32 + lane) * stride);
         for (int u = warp; u < punits; u += kCtWarps) {
           double x0, x1;
@@ -250,6 +261,7 @@ __global__ void __launch_bounds__(kCtThreads, 1)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == nstage) s = 0, ph ^= 1;
       }
       // hand the K+1 partial sums of every vector to the finisher warp
       const int rb = (int)(tcount & 1);
@@ -287,24 +299,42 @@ extern "C" int soap_classify(const void *X, const void *mult, const double *refw
     const int n_units = (dim + ue - 1) / ue;
     const size_t budget = (size_t)max_smem_optin() - 2048;
     if (aligned && n_refs <= kCtMaxK && (dtype == SOAP_F64 || dtype == SOAP_F32)) {
+      // pieces of an odd number of 16-byte units (slots 16*odd bytes apart, <= 127 units = one box row);
+      // as many stages as fit, preferring >= 64 KB in flight per SM and then the fewest pieces
+      int best_upp = 0, best_pieces = 0, best_stage = 0;
+      size_t best_score = 0;
       for (int npieces = 1; npieces <= n_units; ++npieces) {
-        const int upp = (n_units + npieces - 1) / npieces;
+        const int upp = ((n_units + npieces - 1) / npieces) | 1;
+        if (upp > 127 || upp > n_units) continue;
         const int real_pieces = (n_units + upp - 1) / upp;
-        const int stride = 16 * (upp | 1);
         const size_t Dp = (size_t)real_pieces * upp * ue;
-        const size_t fixed = (size_t)(n_refs + 1) * Dp * 8 + (size_t)2 * kCtWarps * (n_refs + 1) * 32 * 8 + 128;
-        const size_t smem_t = (size_t)2 * 32 * stride + fixed;
-        if (fixed + 2 * 32 * 16 * 3 > budget) break;
-        if (smem_t > budget) continue;
+        const size_t fixed = (size_t)(n_refs + 1) * Dp * 8 + (size_t)2 * kCtWarps * (n_refs + 1) * 32 * 8 + 256;
+        for (int st = 4; st >= 2; --st) {
+          if ((size_t)st * 32 * 16 * upp + fixed > budget) continue;
+          size_t score = (size_t)(st - 1) * 32 * 16 * upp;
+          if (score > 65536) score = 65536;
+          if (score > best_score) best_score = score, best_upp = upp, best_pieces = real_pieces, best_stage = st;
+          break;
+        }
+      }
+      if (best_upp > 0) {
+        const int upp = best_upp, real_pieces = best_pieces, stride = 16 * best_upp, nstage = best_stage;
+        const size_t Dp = (size_t)real_pieces * upp * ue;
+        const size_t smem_t = (size_t)nstage * 32 * stride + (size_t)(n_refs + 1) * Dp * 8 +
+                              (size_t)2 * kCtWarps * (n_refs + 1) * 32 * 8 + 256;
         const long long ntiles = (nvec + 31) / 32;
         const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
+        CUtensorMap tmap;
+        int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, nvec, (int64_t)dim * es / 8, stride / 8, 32,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
         ProfScope prof(SOAP_PROF_PAIRS, s);
 #define CT_LAUNCH(T, KM)                                                                                              \
   do {                                                                                                                \
     SOAP_CUDA(cudaFuncSetAttribute(classify_tiled_kernel<T, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
     classify_tiled_kernel<T, KM><<<grid, kCtThreads, smem_t, s>>>(                                                    \
         static_cast<const T *>(X), static_cast<const double *>(mult), refw, ref_norm2, nvec, dim, n_refs, kind, power, \
-        normalize_x, dist_out, argmin_out, min_out, upp, real_pieces, stride);                                        \
+        normalize_x, dist_out, argmin_out, min_out, upp, real_pieces, stride, nstage, tmap);                                        \
   } while (0)
         if (dtype == SOAP_F64) {
           if (n_refs <= 8) CT_LAUNCH(double, 8); else if (n_refs <= 16) CT_LAUNCH(double, 16); else CT_LAUNCH(double, 32);

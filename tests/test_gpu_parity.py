@@ -270,6 +270,49 @@ def test_timesoap_sweep_from_compressed_vs_oracle(S, F, A, species, dtype, windo
                 assert_allclose(eu, np.linalg.norm(X[1:] - X[:-1], axis=-1), rtol=1e-12, atol=1e-15)
 
 
+@pytest.mark.parametrize(
+    "F,A,D,dtype,windows",
+    [
+        (5, 1, 4, np.float64, (1, 2)),        # one box is wider and taller than the whole trajectory
+        (3, 2, 8, np.float32, (1,)),          # fewer frames than a block, fewer blocks than the prefetch depth
+        (33, 1, 18, np.float64, (1, 32)),     # two blocks, the second almost empty
+        (40, 700, 36, np.float64, (1, 3)),    # several work items per persistent CTA (700 > SMs)
+        (64, 450, 250, np.float32, (1, 5, 10, 50)),
+        (97, 160, 1224, np.float64, (1, 5, 10, 50)),  # rows split into pieces, pieces change inside a CTA
+        (35, 5, 7, np.float64, (2, 4)),       # unaligned rows: element-copy path, several items per CTA
+        (35, 300, 7, np.float32, (1, 9)),
+    ],
+)
+def test_timelag_persistent_stream_edge_shapes(S, F, A, D, dtype, windows, monkeypatch):
+    """The timelag kernel walks (atom, piece) items as one continuous stream of 32-frame blocks per CTA;
+    results must not depend on where item boundaries fall, with and without multiplicities."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.analysis import timelag_device
+
+    rng = np.random.default_rng(F * 1000 + A + D)
+    X = rng.random((F, A, D)).astype(dtype)
+    path = "f64" if dtype == np.float64 else "f32"
+    got = S.timeSOAPsweep(X, windows=windows)
+    X64 = X.astype(np.float64)
+    for w, (t, dt) in zip(windows, got):
+        want, _ = O.timeSOAP_batched(X64, window=w, kind=O.KIND_SIMPLE)
+        assert_distance_parity(t, want, path, what=f"w{w}")
+        assert_array_equal(dt, np.diff(t.T, axis=-1))
+    # weighted dots (multiplicities 1 / 2) == plain dots of the vectors scaled by sqrt(m)
+    m = (1.0 + (rng.random(D) < 0.4)).astype(dtype)
+    ts = timelag_device(torch.from_numpy(X).cuda(), windows, _lib.KIND_SIMPLE, 1, mult=torch.from_numpy(m).cuda())
+    Xw = X64 * np.sqrt(m.astype(np.float64))
+    for w, t in zip(windows, ts):
+        want, _ = O.timeSOAP_batched(Xw, window=w, kind=O.KIND_SIMPLE)
+        assert_distance_parity(t.cpu().numpy(), want, path, what=f"weighted w{w}")
+    # the same call squeezed onto two CTAs (every CTA streams many items): bit-identical results
+    monkeypatch.setenv("SOAP_TL_GRID", "2")
+    ts2 = timelag_device(torch.from_numpy(X).cuda(), windows, _lib.KIND_SIMPLE, 1, mult=torch.from_numpy(m).cuda())
+    for t, t2 in zip(ts, ts2):
+        assert_array_equal(t.cpu().numpy(), t2.cpu().numpy())
+
+
 def test_host_trajectory_larger_than_budget_is_tiled_over_atoms(S, monkeypatch):
     """host inputs that do not fit the device budget are processed in atom tiles (same results)."""
     from cpctools_b200 import analysis
