@@ -96,12 +96,13 @@ def load() -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("SOAP_B200_LIB", LIB_PATH)  # A/B benchmarking of two builds
+        if not os.path.exists(path):
             raise SoapB200Error(
-                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(cpctools_b200 has no CPU fallback)"
             )
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the ABI and the header disagree
             fn.restype, fn.argtypes = res, args
