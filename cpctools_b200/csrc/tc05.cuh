@@ -96,7 +96,8 @@ inline EncodeTiledFn encode_tiled_fn() {
 
 // 2-D row-major matrix [rows][row_bytes / elem] -> tiles of box_rows x box_inner elements, swizzled
 inline int make_tensor_map_2d(CUtensorMap *map, const void *base, CUtensorMapDataType dt, int elem_bytes, int64_t rows,
-                              int64_t row_elems, int box_inner, int box_rows, CUtensorMapSwizzle swz) {
+                              int64_t row_elems, int box_inner, int box_rows, CUtensorMapSwizzle swz,
+                              CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return set_error(SOAP_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)row_elems, (cuuint64_t)rows};
@@ -104,7 +105,7 @@ inline int make_tensor_map_2d(CUtensorMap *map, const void *base, CUtensorMapDat
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(SOAP_ECUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
   return SOAP_OK;
 }
