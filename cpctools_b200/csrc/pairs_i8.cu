@@ -24,6 +24,7 @@
 #include "tc05.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -32,6 +33,7 @@ namespace soapb {
 constexpr int kI8BM = 128;
 constexpr int kI8EpiWarps = 8;                       // two per TMEM lane quarter: latency hiding in the epilogue
 constexpr int kI8Threads = 64 + 32 * kI8EpiWarps;
+constexpr int kI8StagePitch = 80;  // bytes per staged row: 64 + 16 pad (16 * odd: conflict-free 128-bit access)
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -44,6 +46,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
+}
+// exact int64 -> double for |x| < 2^51 without the slow I2F.F64.S64: add the integer to the bit pattern of
+// 1.5 * 2^52 (its ulp is 1) and subtract that constant again
+__device__ __forceinline__ double exact_i2d(long long x) {
+  return __longlong_as_double(x + 0x4338000000000000ll) - 6755399441055744.0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -151,6 +158,9 @@ __global__ void __launch_bounds__(kI8Threads, 1)
   uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + ACC);
   int *col_exp = reinterpret_cast<int *>(smem + (size_t)STAGES * STAGE_BYTES + 256);  // [kI8EpiWarps][BN] (FAST path)
   double *col_rn = reinterpret_cast<double *>(col_exp + kI8EpiWarps * BN);            // [kI8EpiWarps][BN], cosine kinds only
+  // FAST epilogues: per-warp [32 rows][64 + 16 pad bytes] tile that turns a chunk of the accumulator
+  // (lane = row) into row-contiguous 64-byte stores
+  unsigned char *epi_stage = reinterpret_cast<unsigned char *>(col_rn + kI8EpiWarps * BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // symmetric mode (data is spectra): only tiles that reach the upper triangle are listed, and every
@@ -274,10 +284,36 @@ __global__ void __launch_bounds__(kI8Threads, 1)
         double *my_rn = col_rn + (warp - 2) * BN;
         const bool cosine = (kind != SOAP_KIND_NORMALIZED);
         const double ri = (cosine && row_ok) ? rsqrt(uu[row]) : 1.0;  // 1/|x_i|; a zero vector gives inf -> NaN like 0/0
-        for (int cidx = lane; cidx < BN; cidx += 32) {
-          const long long col = (long long)tn * BN + cidx;
-          my_exp[cidx] = col < N ? ((__double2hiint(sb[col]) >> 20) & 0x7ff) : 0x7ff;
-          if (cosine) my_rn[cidx] = col < N ? rsqrt(vv[col]) : 1.0;
+        // When every scale exponent of this warp's rows and of the tile's columns is moderate (always, for
+        // data of ordinary magnitude) the power-of-two factors are staged as floats: c_j = -2 * 2^(e_j - 1023),
+        // and an output costs  3 I2F + 3 FFMA + 1 FMUL + 1 MUFU.  Otherwise the exponents are staged as
+        // integers and combined with clamping / NaN propagation per output (general path).
+        bool lean = false;
+        if constexpr (ND == 3) {
+          bool ok = !cosine && (!row_ok || (ei >= 1023 - 60 && ei <= 1023 + 60));
+          int ejs[(BN + 31) / 32];
+#pragma unroll
+          for (int r = 0; r < (BN + 31) / 32; ++r) {
+            const int cidx = lane + 32 * r;
+            const long long col = (long long)tn * BN + cidx;
+            ejs[r] = (cidx < BN && col < N) ? ((__double2hiint(sb[col]) >> 20) & 0x7ff) : 1023;
+            ok = ok && (ejs[r] >= 1023 - 60 && ejs[r] <= 1023 + 60);
+          }
+          lean = __all_sync(0xffffffffu, ok);
+          if (lean) {
+#pragma unroll
+            for (int r = 0; r < (BN + 31) / 32; ++r) {
+              const int cidx = lane + 32 * r;
+              if (cidx < BN) my_exp[cidx] = (int)(0x80000000u | (uint32_t)((ejs[r] - 1023 + 128) << 23));  // -2^(e+1)
+            }
+          }
+        }
+        if (!lean) {
+          for (int cidx = lane; cidx < BN; cidx += 32) {
+            const long long col = (long long)tn * BN + cidx;
+            my_exp[cidx] = col < N ? ((__double2hiint(sb[col]) >> 20) & 0x7ff) : 0x7ff;
+            if (cosine) my_rn[cidx] = col < N ? rsqrt(vv[col]) : 1.0;
+          }
         }
         __syncwarp();
         mbar_wait_guard(&tmem_full[as], (uint32_t)((it / ACC) & 1));
@@ -285,6 +321,68 @@ __global__ void __launch_bounds__(kI8Threads, 1)
         const uint32_t taddr = tmem_base + (uint32_t)(as * ND * BN) + ((uint32_t)(q * 32) << 16);
         if constexpr (ND == 3) {
           const bool vec4 = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+          if (lean) {
+            const float prow = __int_as_float((ei - 1023 + 127) << 23);
+#pragma unroll 1
+            for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 16); c += PARTS) {
+              uint32_t v[ND][16];
+#pragma unroll
+              for (int g = 0; g < ND; ++g) tmem_ld16(taddr + (uint32_t)(g * BN + c * 16), v[g]);
+              float cj[16];
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 c4 = *reinterpret_cast<const float4 *>(my_exp + c * 16 + j);
+                cj[j] = c4.x; cj[j + 1] = c4.y; cj[j + 2] = c4.z; cj[j + 3] = c4.w;
+              }
+              tmem_ld_wait();
+              const long long col0 = (long long)tn * BN + c * 16;
+              // a lane owns a ROW of the accumulator: storing from registers sends 32 requests of 16 bytes per
+              // instruction to L2, one per clock (measured: 0.55 of 2.1 ms exposed).  The chunk goes through a
+              // padded shared-memory tile instead and leaves as 64 contiguous bytes per row (4 lanes each).
+              // (A TMA tile store of the same chunk measured slower: the proxy fence sits on the critical path.)
+              float *stg = reinterpret_cast<float *>(epi_stage + (warp - 2) * (32 * kI8StagePitch));
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                float o[4];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const int jj = j + k4;
+                  const float tf = fmaf(fmaf((float)(int)v[2][jj], 1.0f / 256.0f, (float)(int)v[1][jj]), 1.0f / 256.0f,
+                                        (float)(int)v[0][jj]);
+                  // 2 - 2 g with g = tf * 2^(e_i + e_j): the scaling is exact, so this is the general path's value
+                  asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(prow * cj[jj], tf, 2.0f))));
+                }
+                *reinterpret_cast<float4 *>(stg + lane * (kI8StagePitch / 4) + j) = make_float4(o[0], o[1], o[2], o[3]);
+                if (symmetric && row_ok) {  // out[col][row]: the 32 lanes of a warp write 32 consecutive rows
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4)
+                    if (col0 + j + k4 < N) reinterpret_cast<float *>(out)[(size_t)(col0 + j + k4) * ldo + row] = o[k4];
+                }
+              }
+              __syncwarp();
+              if (!(debug_flags & 4)) {
+                const int cq = (lane & 3) * 4;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                  const int r = 8 * m + (lane >> 2);
+                  const long long grow = (long long)tm * BM + q * 32 + r;
+                  const float4 val = *reinterpret_cast<const float4 *>(stg + r * (kI8StagePitch / 4) + cq);
+                  if (grow < M) {
+                    float *dst = reinterpret_cast<float *>(out) + (size_t)grow * ldo + col0 + cq;
+                    if (vec4 && col0 + cq + 4 <= N) {
+                      *reinterpret_cast<float4 *>(dst) = val;
+                    } else {
+                      if (col0 + cq + 0 < N) dst[0] = val.x;
+                      if (col0 + cq + 1 < N) dst[1] = val.y;
+                      if (col0 + cq + 2 < N) dst[2] = val.z;
+                      if (col0 + cq + 3 < N) dst[3] = val.w;
+                    }
+                  }
+                }
+              }
+              __syncwarp();
+            }
+          } else
 #pragma unroll 1
           for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 16); c += PARTS) {
             uint32_t v[ND][16];
@@ -351,6 +449,8 @@ __global__ void __launch_bounds__(kI8Threads, 1)
             }
             tmem_ld_wait();
             const long long col0 = (long long)tn * BN + c * 8;
+            // (staging this chunk through shared memory like the fp32 one measured slower: the fp64 epilogue is
+            // bound by its arithmetic, the stores cost 0.3 of 7.8 ms)
             double *dst = reinterpret_cast<double *>(out) + (size_t)row * ldo + col0;
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
@@ -363,7 +463,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
                 for (int g = 0; g < ND / 2; ++g) hi = hi * 256 + (long long)(int)v[g][jj];
 #pragma unroll
                 for (int g = ND / 2; g < ND; ++g) lo = lo * 256 + (long long)(int)v[g][jj];
-                const double tsum = fma((double)lo, kLo, (double)hi * kHi);
+                const double tsum = fma(exact_i2d(lo), kLo, exact_i2d(hi) * kHi);
                 int k = ei + ej[jj] - 2 * 1023;
                 k = k < -1022 ? -1022 : (k > 1023 ? 1023 : k);
                 const double pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __longlong_as_double(0x7ff8000000000000ll)
@@ -538,13 +638,13 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   // the reciprocal-norm staging only exists for the cosine kinds (it would not fit beside 4 stages)
   const size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)kI8EpiWarps * BN * 4 +
-                      ((FAST && kind != SOAP_KIND_NORMALIZED) ? (size_t)kI8EpiWarps * BN * 8 : 0);
+                      (FAST ? (size_t)kI8EpiWarps * (BN * 8 + 32 * kI8StagePitch) : 0);
   SOAP_REQUIRE(SMEM <= (size_t)max_smem_optin(), "soap_pairs: internal: tile configuration exceeds shared memory");
   auto kern = tile_list ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, FAST, OutT>
                         : pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, false, OutT>;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   ProfScope prof(SOAP_PROF_PAIRS, s);
-  const char *dbg = getenv("SOAP_I8_DEBUG");  // experiments: 1 = skip the epilogue, 2 = one MMA per K block
+  const char *dbg = getenv("SOAP_I8_DEBUG");  // experiments: 1 = skip the epilogue, 2 = one MMA per K block, 4 = no stores
   kern<<<grid, kI8Threads, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n,
                                       dbg ? atoi(dbg) : 0, tile_list, n_listed);
   return check_launch("pairs_i8_kernel");
@@ -573,7 +673,7 @@ int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t 
       case 1: return I8_LAUNCH(float, 3, 160, 128, 1, 2, true, float);
       case 2: return I8_LAUNCH(float, 3, 80, 64, 2, 4, true, float);
       case 3: return I8_LAUNCH(float, 3, 80, 128, 2, 2, true, float);
-      default: return I8_LAUNCH(float, 3, 160, 64, 1, 4, true, float);
+      default: return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, float);
     }
   }
   return I8_LAUNCH(float, 3, 80, 128, 2, 2, false, float);
