@@ -140,29 +140,49 @@ def cpu_info():
     return info
 
 
+def _ref_worker(job):
+    """one host process = one shard of atoms (the reference loops are single-threaded Python; every
+    atom's time series is independent, so this is the same sharding the GPU arm uses across GPUs)"""
+    frames, atoms, seed, steps = job
+    raw, slices = cpu_sample(frames, atoms, seed=seed)
+    pairs = 0
+    for _ in range(steps):
+        pairs += cpu_reference_step(raw, slices)
+    return pairs
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import multiprocessing as mp
+
     frames, atoms = args.ref_frames, args.ref_atoms
-    raw, slices = cpu_sample(frames, atoms)
-    for _ in range(args.warmup):
-        cpu_reference_step(raw[:80], slices)  # warm-up on a slice: imports, caches, BLAS threads
-    t0 = time.perf_counter()
-    pairs = 0
-    for _ in range(args.steps):
-        pairs += cpu_reference_step(raw, slices)
-    dt = time.perf_counter() - t0
+    procs = args.ref_procs if args.ref_procs > 0 else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = "1"  # one BLAS thread per worker: the workers already fill the cores
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    ctx = mp.get_context("fork")  # no CUDA / torch state exists in this process
+    with ctx.Pool(procs) as pool:
+        # warm-up on a slice: worker start-up, imports, caches
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_ref_worker, [(80, 2, 1000 + i, 1) for i in range(procs)])
+        t0 = time.perf_counter()
+        done = pool.map(_ref_worker, [(frames, atoms, 12345 + i, args.steps) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    pairs = int(sum(done))
     value = pairs / dt
     info = cpu_info()
-    sample = f"{frames} frames x {atoms} atoms x Dc 1224 fp64 per step ({pairs // args.steps} pairs), full pipeline fill+normalise+4x timeSOAP"
+    info["cores"] = procs
+    sample = (f"{procs} host processes x {args.steps} steps x ({frames} frames x {atoms} atoms x Dc 1224 fp64, "
+              f"{pairs // (args.steps * procs)} pairs): full pipeline fill+normalise+4x timeSOAP per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "timeSOAP delay sweep (1,5,10,50), 2 species nMax=lMax=8 (Dc 1224 -> Df 1728), reference "
                                "algorithm (oracle port of SOAPify: numpy gather, numpy normalise, Python loop + scipy cosine) "
-                               "on host cores; bounded sample of the GPU arm's workload", "sample": sample},
+                               "on all host cores, atoms sharded over processes; bounded sample of the GPU arm's workload",
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "kind": "port", "sample": sample, **info},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -470,7 +490,8 @@ def main():
     ap.add_argument("--atoms", type=int, default=ATOMS_PER_GPU, help="atoms per GPU of the resident tile")
     ap.add_argument("--e2e-atoms", type=int, default=1250, help="atoms per GPU of the host-resident end-to-end tile")
     ap.add_argument("--ref-frames", type=int, default=1000)
-    ap.add_argument("--ref-atoms", type=int, default=24, help="atoms of the bounded CPU sample per step")
+    ap.add_argument("--ref-atoms", type=int, default=24, help="atoms of the bounded CPU sample per step and host process")
+    ap.add_argument("--ref-procs", type=int, default=0, help="host processes of the reference arm (0 = all cores)")
     ap.add_argument("--cpu-atoms", type=int, default=150, help="atoms of the cpu_baseline sample inside the GPU arm (~10 s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-allpairs", action="store_true")
