@@ -47,6 +47,9 @@ SIGNATURES = {
     "soap_classify": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "soap_transition_counts": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "soap_residence_capacity": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
+    "soap_residence_events": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_void_p]),
     "soap_fill_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_int, c_void_p]),
 }
 

@@ -1,4 +1,4 @@
-// transitions.cu -- f4: unnormalised transition matrix of a classification.
+// transitions.cu -- f4: unnormalised transition matrix and residence times of a classification.
 //
 // Reference semantics: transitionMatrixFromSOAPClassification
 // (src/SOAPify/transitions/__init__.py:9-48):
@@ -43,9 +43,73 @@ __global__ void __launch_bounds__(kTrThreads)
   }
 }
 
+// Residence times of a classification: calculateResidenceTimesFromClassification
+// (src/SOAPify/transitions/__init__.py:99-167).  One thread owns one series = (atom, initial frame):
+// it walks the frames initial + k*window and emits (state, time) whenever the state changes, the
+// first interval of a series negated, plus the closing  -(time + window)  of the open interval.
+// Consecutive threads are consecutive atoms, so every frame row is read coalesced.  Events go to one
+// global list (slot = atomic cursor); the reference returns them SORTED per state, so their order of
+// production is irrelevant (the host sorts on the device).
+__global__ void __launch_bounds__(256)
+    residence_events_kernel(const int *__restrict__ states, long long n_frames, long long n_atoms, int n_classes,
+                            long long window, long long stride, int n_init, int *__restrict__ ev_state,
+                            long long *__restrict__ ev_time, long long capacity, unsigned long long *__restrict__ cursor) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_atoms * n_init) return;
+  const long long atom = i % n_atoms;
+  const long long initial = (i / n_atoms) * stride;
+  auto emit = [&](int st, long long t) {
+    const unsigned long long slot = atomicAdd(cursor, 1ull);
+    if ((long long)slot < capacity) {
+      ev_state[slot] = st;
+      ev_time[slot] = t;
+    }
+  };
+  long long time = 0;
+  int state = states[initial * n_atoms + atom];
+  bool first = true;
+  for (long long f = window + initial; f < n_frames; f += window) {
+    time += window;
+    const int now = states[f * n_atoms + atom];
+    if (now != state) {
+      emit(state, first ? -time : time);
+      first = false;
+      state = now;
+      time = 0;
+    }
+  }
+  emit(state, -time - window);  // the open interval at the end of the series
+}
+
 }  // namespace soapb
 
 using namespace soapb;
+
+extern "C" int64_t soap_residence_capacity(int64_t n_frames, int64_t n_atoms, int64_t window, int64_t stride) {
+  if (n_frames <= 0 || n_atoms <= 0 || window < 1 || stride < 1) return 0;
+  const int64_t n_init = (window + stride - 1) / stride;            // len(range(0, window, stride))
+  return n_atoms * n_init * (n_frames / window + 2);                 // visited frames + the closing event
+}
+
+extern "C" int soap_residence_events(const int32_t *states, int64_t n_frames, int64_t n_atoms, int n_classes,
+                                     int64_t window, int64_t stride, int32_t *ev_state, int64_t *ev_time,
+                                     int64_t capacity, uint64_t *n_events, void *stream) {
+  SOAP_REQUIRE(n_frames > 0 && n_atoms > 0 && n_classes > 0, "soap_residence_events: bad shape");
+  SOAP_REQUIRE(window >= 1 && stride >= 1 && stride <= window && window <= n_frames,
+               "soap_residence_events: bad window / stride");
+  SOAP_REQUIRE(states && ev_state && ev_time && n_events, "soap_residence_events: null buffer");
+  SOAP_REQUIRE(capacity >= soap_residence_capacity(n_frames, n_atoms, window, stride),
+               "soap_residence_events: capacity %lld is below soap_residence_capacity()", (long long)capacity);
+  auto s = static_cast<cudaStream_t>(stream);
+  SOAP_CUDA(cudaMemsetAsync(n_events, 0, sizeof(uint64_t), s));
+  const int64_t n_init = (window + stride - 1) / stride;
+  const int64_t series = n_atoms * n_init;
+  SOAP_REQUIRE(n_init < (1ll << 31) && (series + 255) / 256 < (1ll << 31), "soap_residence_events: too many series");
+  residence_events_kernel<<<(unsigned)((series + 255) / 256), 256, 0, s>>>(
+      states, n_frames, n_atoms, n_classes, window, stride, (int)n_init, ev_state, reinterpret_cast<long long *>(ev_time),
+      capacity, reinterpret_cast<unsigned long long *>(n_events));
+  return check_launch("residence_events_kernel");
+}
 
 extern "C" int soap_transition_counts(const int32_t *states, int64_t n_frames, int64_t n_atoms, int n_classes,
                                       int64_t window, int64_t stride, uint64_t *counts, void *stream) {

@@ -144,6 +144,19 @@ int soap_classify(const void *X, const void *mult, const double *refw, const dou
 int soap_transition_counts(const int32_t *states, int64_t n_frames, int64_t n_atoms, int n_classes, int64_t window,
                            int64_t stride, uint64_t *counts, void *stream);
 
+/* ---- residence times of a classification: calculateResidenceTimesFromClassification,
+ * transitions/__init__.py:99-167.  For every atom and every initial frame in range(0, window, stride)
+ * the series states[initial + k*window][atom] is walked; each change of state emits (old state, time
+ * spent), the first interval of a series negated, and every series closes with -(time + window).
+ * Events are appended in no particular order (the reference sorts them per state) to
+ * ev_state[] / ev_time[]; *n_events receives their number.  capacity must be at least
+ * soap_residence_capacity().  Integer work, bit-exact.
+ */
+int64_t soap_residence_capacity(int64_t n_frames, int64_t n_atoms, int64_t window, int64_t stride);
+int soap_residence_events(const int32_t *states, int64_t n_frames, int64_t n_atoms, int n_classes, int64_t window,
+                          int64_t stride, int32_t *ev_state, int64_t *ev_time, int64_t capacity, uint64_t *n_events,
+                          void *stream);
+
 /* ---- synthetic data for the benchmarks (counter-based hash RNG, reproducible) ------------
  * fills n elements of `dtype` with uniform [0,1) values derived from (seed, element index).
  */

@@ -221,6 +221,16 @@ def gen_transitions(S):
         tag = f"s{stride}_w{window}"
         out["tm_" + tag] = S.transitionMatrixFromSOAPClassification(data, stride, window)
         out["tmn_" + tag] = S.transitionMatrixFromSOAPClassificationNormalized(data, stride, window)
+    # residence times (transitions/__init__.py:99-167): one sorted array per state; a slowly changing
+    # classification as well, so that long runs exist
+    slow = np.repeat(rng.integers(0, 5, size=(12, 17)), 5, axis=0)
+    out["refs_slow"] = slow
+    for name, arr in (("", refs), ("slow_", slow)):
+        cls = S.SOAPclassification(np.zeros(arr.shape), arr, ["a", "b", "c", "d", "e"])
+        for window, stride in ((1, None), (3, None), (4, 2), (5, 1), (60, 7), (59, 59)):
+            rts = S.calculateResidenceTimesFromClassification(cls, window=window, stride=stride)
+            for state, times in enumerate(rts):
+                out[f"rt_{name}w{window}_s{stride}_{state}"] = np.asarray(times)
     return out
 
 

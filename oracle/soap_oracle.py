@@ -359,6 +359,33 @@ def transitionMatrixFromSOAPClassification(references, n_classes, stride=1, wind
     return mat
 
 
+def calculateResidenceTimesFromClassification(references, n_classes, window=1, stride=None):
+    """Sorted residence times per state (transitions/__init__.py:99-167).  For every atom and every
+    initial frame in range(0, window, stride) the states sampled every ``window`` frames are run-length
+    encoded: a run that ends contributes its length in frames, negated if it is the first run of the
+    series; the run still open at the end contributes ``-(length + window)``."""
+    if stride is None:
+        stride = window
+    if stride > window:
+        raise ValueError("the window must be bigger than the stride")
+    n_frames, n_atoms = references.shape
+    if window > n_frames or stride > n_frames:
+        raise ValueError("stride and window must be smaller than simulation lenght")
+    per_state = [[] for _ in range(n_classes)]
+    for atom in range(n_atoms):
+        series = references[:, atom]
+        for start in range(0, window, stride):
+            current, elapsed, first_run = series[start], 0, True
+            for frame in range(start + window, n_frames, window):
+                elapsed += window
+                if series[frame] != current:
+                    per_state[current].append(-elapsed if first_run else elapsed)
+                    first_run = False
+                    current, elapsed = series[frame], 0
+            per_state[current].append(-elapsed - window)
+    return [np.sort(np.array(times)) for times in per_state]
+
+
 def normalizeMatrixByRow(transMat):
     """Rows summing to 1, empty rows left at zero (transitions/__init__.py:51-69)."""
     out = transMat.copy()

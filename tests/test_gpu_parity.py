@@ -699,6 +699,43 @@ def test_transition_matrix_matches_golden_and_oracle(S, golden):
 
 
 # ------------------------------------------------------------------ randomised shapes (seeded fuzz)
+def test_residence_times_match_golden_and_oracle(S, golden):
+    g = golden("transitions")
+    cases = ((1, None), (3, None), (4, 2), (5, 1), (60, 7), (59, 59))
+    for name, key in (("", "refs"), ("slow_", "refs_slow")):
+        refs = g[key]
+        data = S.SOAPclassification(np.zeros(refs.shape), refs, ["a", "b", "c", "d", "e"])
+        for window, stride in cases:
+            got = S.calculateResidenceTimesFromClassification(data, window=window, stride=stride)
+            assert len(got) == 5
+            for state, times in enumerate(got):
+                want = g[f"rt_{name}w{window}_s{stride}_{state}"]
+                assert_array_equal(times, want)
+                assert times.dtype == want.dtype
+        assert_array_equal(np.concatenate(S.calculateResidenceTimes(data, window=3)),
+                           np.concatenate(S.calculateResidenceTimesFromClassification(data, window=3)))
+    data = S.SOAPclassification(np.zeros(g["refs"].shape), g["refs"], ["a", "b", "c", "d", "e"])
+    with pytest.raises(ValueError, match="the window must be bigger than the stride"):
+        S.calculateResidenceTimesFromClassification(data, window=2, stride=3)
+    with pytest.raises(ValueError, match="stride and window must be smaller"):
+        S.calculateResidenceTimesFromClassification(data, window=61)
+    with pytest.raises(NotImplementedError):
+        S.calculateResidenceTimes(data, statesTracker=[object()])
+    assert_array_equal(S.calculateTransitionMatrix(data, stride=2, window=7), g["tm_s2_w7"])
+    # a large slowly changing classification against the oracle; a state that never occurs gives the
+    # reference's empty float64 array; every frame of every series is accounted for
+    rng = np.random.default_rng(3)
+    big = np.repeat(rng.integers(0, 6, size=(40, 1500)), 7, axis=0)  # 280 frames, runs of >= 7
+    bd = S.SOAPclassification(np.zeros(big.shape), big, list("abcdefg"))
+    for window, stride in ((1, None), (2, 1), (7, 3)):
+        got = S.calculateResidenceTimesFromClassification(bd, window=window, stride=stride)
+        want = O.calculateResidenceTimesFromClassification(big, 7, window=window, stride=stride)
+        for a, b in zip(got, want):
+            assert_array_equal(a, b)
+            assert a.dtype == b.dtype
+        assert got[6].size == 0 and got[6].dtype == np.float64
+
+
 def test_fuzz_random_shapes_against_oracle(S):
     """40 seeded random cases over odd/even dimensions, tiny and ragged frame / atom counts, one to
     four windows, both dtypes, with and without expansion: the time-lag kernel (both staging paths),
