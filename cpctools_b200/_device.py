@@ -73,9 +73,10 @@ def to_host(t) -> np.ndarray:
 
 
 def like_input(result, original):
-    """Return ``result`` (CUDA tensor) in the container type of ``original``."""
+    """Return ``result`` (CUDA tensor) in the container type of ``original``: CUDA tensor -> CUDA
+    tensor (stays on the device), host tensor -> host tensor, anything else -> numpy."""
     if is_tensor(original):
-        return result
+        return result if original.is_cuda else result.cpu()
     return to_host(result)
 
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "soap_residence_capacity": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
     "soap_residence_events": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                       c_void_p, c_void_p]),
+    "soap_copy_rows": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_void_p]),
     "soap_fill_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_int, c_void_p]),
 }
 

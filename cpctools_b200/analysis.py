@@ -119,6 +119,8 @@ def _tiled(x, windows, kind, power, mult, returnDiff):
     F, D = int(x.shape[0]), int(x.shape[2])
     itemsize = 4 if str(getattr(x, "dtype", "")).endswith("float32") else 8
     per_atom = F * D * itemsize + F * 8 * (len(windows) + 1) * 8
+    if _pinned_host_tensor(x) and F * int(x.shape[1]) * D * itemsize >= PIPELINE_MIN_BYTES:
+        return _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom)
     tiles = _atom_tiles(x, per_atom)
     if len(tiles) == 1:
         X = _device.as_float_tensor(x)
@@ -139,6 +141,81 @@ def _tiled(x, windows, kind, power, mult, returnDiff):
         else:
             res.append(th.cat(parts, dim=1) if _device.is_tensor(x) else np.concatenate(parts, axis=1))
     return res
+
+
+#: pinned host trajectories at least this large are uploaded in atom tiles while the previous tile computes
+PIPELINE_MIN_BYTES = 256 << 20
+#: target size of one uploaded atom tile
+PIPELINE_TILE_BYTES = 1 << 30
+
+
+def _pinned_host_tensor(x) -> bool:
+    return (_device.is_tensor(x) and not x.is_cuda and x.dim() == 3 and x.is_contiguous() and x.is_pinned()
+            and x.dtype in (_device.torch.float32, _device.torch.float64))
+
+
+def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom):
+    """Pinned host trajectory -> host results with the link kept busy: atom tiles ``x[:, lo:hi, :]`` are
+    uploaded on a copy stream (strided ``cudaMemcpy2DAsync`` into one of two device buffers) while the
+    previous tile is processed, and every tile's results are downloaded while the next uploads.
+    The step then costs the H2D time of ``x`` plus the tail of the last tile."""
+    th = _device.require_cuda()
+    lib = _lib.load()
+    F, A, D = (int(v) for v in x.shape)
+    es = x.element_size()
+    free, _ = th.cuda.mem_get_info()
+    n_tiles = max(2, -(-F * A * D * es // PIPELINE_TILE_BYTES))
+    while n_tiles < A and 2 * -(-A // n_tiles) * per_atom > 0.5 * free:
+        n_tiles *= 2
+    tile = -(-A // min(n_tiles, A))
+    ranges = [(lo, min(A, lo + tile)) for lo in range(0, A, tile)]
+    bufs = [th.empty((F, tile, D), dtype=x.dtype, device="cuda") for _ in range(2)]
+    copy_stream = th.cuda.Stream()
+    main = th.cuda.current_stream()
+    copied = [th.cuda.Event() for _ in ranges]
+    done = [th.cuda.Event() for _ in ranges]
+    t_host = [th.empty((F - w, A), dtype=th.float64) for w in windows]
+    dt_host = [th.empty((A, F - w - 1), dtype=th.float64) for w in windows] if returnDiff else None
+    pending = []  # device results per tile, kept alive until downloaded
+
+    def upload(i):
+        lo, hi = ranges[i]
+        with th.cuda.stream(copy_stream):
+            if i >= 2:
+                copy_stream.wait_event(done[i - 2])  # the tile that last used this buffer has been consumed
+            rc = lib.soap_copy_rows(
+                bufs[i & 1].data_ptr(), (hi - lo) * D * es, x.data_ptr() + lo * D * es, A * D * es, (hi - lo) * D * es, F, 1,
+                int(copy_stream.cuda_stream),
+            )
+            _lib.check(rc, "soap_copy_rows")
+            copied[i].record(copy_stream)
+
+    def download(i):
+        lo, hi = ranges[i]
+        done[i].synchronize()
+        ts, dts = pending[i]
+        for k in range(len(windows)):
+            t_host[k][:, lo:hi] = ts[k]
+            if returnDiff:
+                dt_host[k][lo:hi] = dts[k]
+        pending[i] = None
+
+    upload(0)
+    for i, (lo, hi) in enumerate(ranges):
+        if i + 1 < len(ranges):
+            upload(i + 1)
+        main.wait_event(copied[i])
+        X = bufs[i & 1][:, : hi - lo, :] if hi - lo == tile else bufs[i & 1].view(-1)[: F * (hi - lo) * D].view(F, hi - lo, D)
+        ts = timelag_device(X, windows, kind, power, mult=mult)
+        dts = [diff_transposed_device(t) for t in ts] if returnDiff else None
+        done[i].record(main)
+        pending.append((ts, dts))
+        if i >= 1:
+            download(i - 1)  # overlaps the upload of tile i + 1
+    download(len(ranges) - 1)
+    if returnDiff:
+        return list(zip(t_host, dt_host))
+    return t_host
 
 
 def _finish(t, like, returnDiff):

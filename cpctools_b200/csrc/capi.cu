@@ -137,3 +137,16 @@ extern "C" int soap_fill_uniform(void *out, int64_t n, uint64_t seed, int dtype,
     return set_error(SOAP_EUNSUPPORTED, "soap_fill_uniform: dtype %d", dtype);
   return check_launch("fill_uniform_kernel");
 }
+
+// strided host <-> device row copy on a stream (cudaMemcpy2DAsync): the atom tiles of a pinned host
+// trajectory [F][A][D] are F rows of (tile atoms * D) elements with a pitch of A * D elements
+extern "C" int soap_copy_rows(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
+                              size_t rows, int to_device, void *stream) {
+  if (row_bytes == 0 || rows == 0) return SOAP_OK;
+  SOAP_REQUIRE(dst && src, "soap_copy_rows: null buffer");
+  SOAP_REQUIRE(dst_pitch >= row_bytes && src_pitch >= row_bytes, "soap_copy_rows: pitch smaller than a row");
+  SOAP_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows,
+                              to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                              static_cast<cudaStream_t>(stream)));
+  return SOAP_OK;
+}

@@ -157,6 +157,12 @@ int soap_residence_events(const int32_t *states, int64_t n_frames, int64_t n_ato
                           int64_t stride, int32_t *ev_state, int64_t *ev_time, int64_t capacity, uint64_t *n_events,
                           void *stream);
 
+/* ---- strided row copy between host and device on a stream (cudaMemcpy2DAsync): used to upload atom
+ * tiles x[:, lo:hi, :] of a pinned host trajectory while the previous tile is being processed.
+ */
+int soap_copy_rows(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes, size_t rows,
+                   int to_device, void *stream);
+
 /* ---- synthetic data for the benchmarks (counter-based hash RNG, reproducible) ------------
  * fills n elements of `dtype` with uniform [0,1) values derived from (seed, element index).
  */

@@ -329,6 +329,33 @@ def test_host_trajectory_larger_than_budget_is_tiled_over_atoms(S, monkeypatch):
     assert_distance_parity(res[1], O.timeSOAP_batched(X, window=2, returnDiff=False), "f64")
 
 
+def test_pinned_host_tensor_is_uploaded_in_overlapped_atom_tiles(S, monkeypatch):
+    """a pinned host tensor takes the pipelined path (strided tile uploads on a copy stream, results
+    downloaded per tile) and returns HOST tensors identical to the one-shot path."""
+    import torch
+    from cpctools_b200 import analysis
+
+    attrs, dc = dscribe_attrs(8, 8, ["H", "O"])
+    kw = dict(atomTypes=["H", "O"], atomicSlices=_slices_from_attrs(attrs))
+    raw = synthetic_soap((70, 37, dc), seed=11, kind="W")
+    want = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1, 5, 50), **kw)
+    pinned = torch.from_numpy(raw).pin_memory()
+    monkeypatch.setattr(analysis, "PIPELINE_MIN_BYTES", 1)
+    monkeypatch.setattr(analysis, "PIPELINE_TILE_BYTES", 5 * 70 * dc * 8)  # 5 atoms per tile: 8 tiles, the last of 2
+    got = S.timeSOAPfromCompressed(pinned, 8, 8, windows=(1, 5, 50), **kw)
+    for (t, dt), (tw, dtw) in zip(got, want):
+        assert isinstance(t, torch.Tensor) and not t.is_cuda and not dt.is_cuda
+        assert_array_equal(t.numpy(), tw)
+        assert_array_equal(dt.numpy(), dtw)
+    only_t = S.timeSOAP(torch.from_numpy(O.normalizeArray(O.fillSOAPVectorFromdscribe(raw, 8, 8, **kw))).pin_memory(),
+                        window=5, returnDiff=False)
+    assert_array_equal(only_t.numpy(), S.timeSOAP(O.normalizeArray(O.fillSOAPVectorFromdscribe(raw, 8, 8, **kw)), window=5, returnDiff=False))
+    # a pageable host tensor keeps the one-shot path, also with host results
+    t2, dt2 = S.timeSOAPfromCompressed(torch.from_numpy(raw), 8, 8, windows=(5,), **kw)[0]
+    assert not t2.is_cuda
+    assert_array_equal(t2.numpy(), S.timeSOAPfromCompressed(raw, 8, 8, windows=(5,), **kw)[0][0])
+
+
 def test_config1_shape_against_the_loop_oracle(S):
     """BASELINE configs[0]: 309 atoms x 200 frames, 1 species (Dc 324 -> Df 576), fp64, the reference's
     own Python-loop path (oracle port) as the checker, default distance and SOAPdistanceNormalized."""
