@@ -31,8 +31,8 @@
 namespace soapb {
 
 constexpr int kI8BM = 128;
-constexpr int kI8EpiWarps = 8;                       // two per TMEM lane quarter: latency hiding in the epilogue
-constexpr int kI8Threads = 64 + 32 * kI8EpiWarps;
+// epilogue warps per CTA (template parameter EW): two per TMEM lane quarter for fp32; three for fp64, whose
+// long fp64 dependency chains profit from more warps (A/B: 7.78 -> 7.56 ms; fp32 1.83 -> 1.85)
 constexpr int kI8StagePitch = 80;  // bytes per staged row: 64 + 16 pad (16 * odd: conflict-free 128-bit access)
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -134,14 +134,15 @@ __device__ __forceinline__ void tile_coords_i8(long long t, int tiles_m, int til
   tn = first + (int)(r % width);
 }
 
-template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, bool SYM, typename OutT>
-__global__ void __launch_bounds__(kI8Threads, 1)
+template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, bool SYM, int EW, bool COS, typename OutT>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
     pairs_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     OutT *__restrict__ out, const double *__restrict__ sa, const double *__restrict__ sb,
                     const double *__restrict__ uu, const double *__restrict__ vv, long long M, long long N, int KB,
                     long long ldo, int kind, int power, int tiles_m, int tiles_n, int debug_flags,
                     const int2 *__restrict__ tile_list, long long n_listed) {
   constexpr int BM = kI8BM;
+  constexpr int kI8EpiWarps = EW;
   constexpr int A_PLANE = BM * BKB, B_PLANE = BN * BKB;
   constexpr int STAGE_BYTES = ND * (A_PLANE + B_PLANE);
   constexpr int KS = BKB / 32;  // UMMA K = 32 for 8-bit operands
@@ -282,29 +283,35 @@ __global__ void __launch_bounds__(kI8Threads, 1)
         const int ei = row_ok ? ((__double2hiint(sa[row]) >> 20) & 0x7ff) : 0x7ff;
         int *my_exp = col_exp + (warp - 2) * BN;
         double *my_rn = col_rn + (warp - 2) * BN;
-        const bool cosine = (kind != SOAP_KIND_NORMALIZED);
+        constexpr bool cosine = COS;  // SIMPLE / KERNEL (normalise inside) vs SOAPdistanceNormalized
         const double ri = (cosine && row_ok) ? rsqrt(uu[row]) : 1.0;  // 1/|x_i|; a zero vector gives inf -> NaN like 0/0
         // When every scale exponent of this warp's rows and of the tile's columns is moderate (always, for
         // data of ordinary magnitude) the power-of-two factors are staged as floats: c_j = -2 * 2^(e_j - 1023),
         // and an output costs  3 I2F + 3 FFMA + 1 FMUL + 1 MUFU.  Otherwise the exponents are staged as
         // integers and combined with clamping / NaN propagation per output (general path).
         bool lean = false;
-        if constexpr (ND == 3) {
-          bool ok = !cosine && (!row_ok || (ei >= 1023 - 60 && ei <= 1023 + 60));
+        if constexpr (!COS) {
+          constexpr int kSpan = ND == 3 ? 60 : 480;  // the product of two factors stays a normal number
+          bool ok = !row_ok || (ei >= 1023 - kSpan && ei <= 1023 + kSpan);
           int ejs[(BN + 31) / 32];
 #pragma unroll
           for (int r = 0; r < (BN + 31) / 32; ++r) {
             const int cidx = lane + 32 * r;
             const long long col = (long long)tn * BN + cidx;
             ejs[r] = (cidx < BN && col < N) ? ((__double2hiint(sb[col]) >> 20) & 0x7ff) : 1023;
-            ok = ok && (ejs[r] >= 1023 - 60 && ejs[r] <= 1023 + 60);
+            ok = ok && (ejs[r] >= 1023 - kSpan && ejs[r] <= 1023 + kSpan);
           }
           lean = __all_sync(0xffffffffu, ok);
           if (lean) {
 #pragma unroll
             for (int r = 0; r < (BN + 31) / 32; ++r) {
               const int cidx = lane + 32 * r;
-              if (cidx < BN) my_exp[cidx] = (int)(0x80000000u | (uint32_t)((ejs[r] - 1023 + 128) << 23));  // -2^(e+1)
+              if (cidx < BN) {  // c_j = -2 * 2^(e_j - 1023) = -2^(e_j - 1022)
+                if constexpr (ND == 3)
+                  my_exp[cidx] = (int)(0x80000000u | (uint32_t)((ejs[r] - 1023 + 128) << 23));
+                else
+                  my_rn[cidx] = __hiloint2double((int)(0x80000000u | (uint32_t)((ejs[r] + 1) << 20)), 0);
+              }
             }
           }
         }
@@ -436,6 +443,7 @@ __global__ void __launch_bounds__(kI8Threads, 1)
           const bool vec2 = ((ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
           constexpr double kHi = 1.0 / (double)(1ull << (8 * (ND / 2 - 1)));
           constexpr double kLo = 1.0 / (double)(1ull << (8 * (ND - 1)));
+          const double prow = __hiloint2double(ei << 20, 0);  // 2^(e_i - 1023), only used when `lean`
 #pragma unroll 1
           for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 8); c += PARTS) {
             uint32_t v[ND][8];
@@ -464,6 +472,10 @@ __global__ void __launch_bounds__(kI8Threads, 1)
 #pragma unroll
                 for (int g = ND / 2; g < ND; ++g) lo = lo * 256 + (long long)(int)v[g][jj];
                 const double tsum = fma(exact_i2d(lo), kLo, exact_i2d(hi) * kHi);
+                if (lean) {  // 2 - 2 g with g = tsum * 2^(e_i + e_j): exact scaling, same value as below
+                  o[k2] = sqrt(fabs(fma(prow * my_rn[c * 8 + jj], tsum, 2.0)));
+                  continue;
+                }
                 int k = ei + ej[jj] - 2 * 1023;
                 k = k < -1022 ? -1022 : (k > 1023 ? 1023 : k);
                 const double pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __longlong_as_double(0x7ff8000000000000ll)
@@ -583,7 +595,7 @@ static size_t i8_scratch_bytes(int64_t M, int64_t N, int D) {
   return align_up((size_t)ND * M * Dp, 1024) + align_up((size_t)ND * N * Dp, 1024) + (size_t)(M + N) * 16 + 4096 + tiles * 8;
 }
 
-template <typename InT, int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, typename OutT>
+template <typename InT, int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, int EW, bool COS, typename OutT>
 static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                            int power, void *scratch, cudaStream_t s) {
   SOAP_REQUIRE(out != nullptr, "soap_pairs: the tensor-core path writes the full matrix (out == NULL)");
@@ -637,22 +649,17 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   }
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   // the reciprocal-norm staging only exists for the cosine kinds (it would not fit beside 4 stages)
-  const size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)kI8EpiWarps * BN * 4 +
-                      (FAST ? (size_t)kI8EpiWarps * (BN * 8 + 32 * kI8StagePitch) : 0);
+  const size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)EW * BN * 4 +
+                      (FAST ? (size_t)EW * (BN * 8 + 32 * kI8StagePitch) : 0);
   SOAP_REQUIRE(SMEM <= (size_t)max_smem_optin(), "soap_pairs: internal: tile configuration exceeds shared memory");
-  auto kern = tile_list ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, FAST, OutT>
-                        : pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, false, OutT>;
+  auto kern = tile_list ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, FAST, EW, COS, OutT>
+                        : pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, false, EW, COS, OutT>;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   ProfScope prof(SOAP_PROF_PAIRS, s);
   const char *dbg = getenv("SOAP_I8_DEBUG");  // experiments: 1 = skip the epilogue, 2 = one MMA per K block, 4 = no stores
-  kern<<<grid, kI8Threads, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n,
+  kern<<<grid, 64 + 32 * EW, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n,
                                       dbg ? atoi(dbg) : 0, tile_list, n_listed);
   return check_launch("pairs_i8_kernel");
-}
-
-static int env_variant() {
-  const char *v = getenv("SOAP_I8_VARIANT");  // 1 = single accumulator set with wide tiles (experiments)
-  return v ? atoi(v) : 0;
 }
 
 size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
@@ -660,37 +667,24 @@ size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
   return dtype == SOAP_F64 ? i8_scratch_bytes<6, 128>(M, N, D) : i8_scratch_bytes<3, 128>(M, N, D);
 }
 
-#define I8_LAUNCH(IN, ND, BN, BKB, ACC, ST, FAST, OUT) \
-  launch_pairs_i8<IN, ND, BN, BKB, ACC, ST, FAST, OUT>(A, B, out, M, N, D, ldo, kind, power, scratch, s)
+#define I8_LAUNCH(IN, ND, BN, BKB, ACC, ST, FAST, EW, COS, OUT) \
+  launch_pairs_i8<IN, ND, BN, BKB, ACC, ST, FAST, EW, COS, OUT>(A, B, out, M, N, D, ldo, kind, power, scratch, s)
 
+// Tile shapes measured on 25 000^2 x 576 (ms, first version of the epilogue), fp32: N160/K64/4 stages 2.19 |
+// N80/K64/4 stages, 2 accumulator sets 2.33 | N160/K128/2 stages 2.35 | N80/K128/2 stages, 2 sets 2.41;
+// fp64: N80/K64/2 stages is the best of N32 (2 sets) / N80 K32 4 stages / N64 3 stages.
 int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
-  if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, float);
-  if (kind == SOAP_KIND_NORMALIZED) {
-    // measured on 25 000^2 x 576 (ms): N160/K64/4 stages 2.19 | N80/K64/4 stages, 2 acc. sets 2.33 |
-    // N160/K128/2 stages 2.35 | N80/K128/2 stages, 2 acc. sets 2.41
-    switch (env_variant()) {
-      case 1: return I8_LAUNCH(float, 3, 160, 128, 1, 2, true, float);
-      case 2: return I8_LAUNCH(float, 3, 80, 64, 2, 4, true, float);
-      case 3: return I8_LAUNCH(float, 3, 80, 128, 2, 2, true, float);
-      default: return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, float);
-    }
-  }
-  return I8_LAUNCH(float, 3, 80, 128, 2, 2, false, float);
+  if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, 8, true, float);
+  if (kind == SOAP_KIND_NORMALIZED) return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, 8, false, float);
+  return I8_LAUNCH(float, 3, 80, 128, 2, 2, false, 8, true, float);
 }
 
 int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                  int power, void *scratch, cudaStream_t s) {
-  if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, double);
-  if (kind == SOAP_KIND_NORMALIZED) {
-    switch (env_variant()) {
-      case 1: return I8_LAUNCH(double, 6, 32, 64, 2, 2, true, double);
-      case 2: return I8_LAUNCH(double, 6, 80, 32, 1, 4, true, double);
-      case 3: return I8_LAUNCH(double, 6, 64, 64, 1, 3, true, double);
-      default: return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, double);
-    }
-  }
-  return I8_LAUNCH(double, 6, 80, 64, 1, 2, false, double);
+  if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, 12, true, double);
+  if (kind == SOAP_KIND_NORMALIZED) return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, 12, false, double);
+  return I8_LAUNCH(double, 6, 80, 64, 1, 2, false, 8, true, double);
 }
 #undef I8_LAUNCH
 
