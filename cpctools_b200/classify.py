@@ -151,10 +151,7 @@ def _prepared_blocks(SOAPTrajData, references: SOAPReferences, doNormalize: bool
         lo, hi = max(lo, first), min(hi, last)
         if lo >= hi:
             continue
-        host = np.asarray(SOAPTrajData[lo:hi])
-        if host.dtype not in (np.float32, np.float64):
-            host = host.astype(np.float64)
-        raw = up.put(host)
+        raw = up.put_frames(SOAPTrajData, lo, hi)
         rows = raw.reshape(-1, Dc)
         if convert or doNormalize:
             out = th.empty((rows.shape[0], Dref), dtype=rows.dtype, device="cuda")
@@ -214,10 +211,7 @@ def _fused_blocks(SOAPTrajData, setup, kind, power, doNormalize, want_dist, fram
         lo, hi = max(lo, first), min(hi, last)
         if lo >= hi:
             continue
-        host = np.asarray(SOAPTrajData[lo:hi])
-        if host.dtype not in (np.float32, np.float64):
-            host = host.astype(np.float64)
-        rows = up.put(host).reshape(-1, Dc)
+        rows = up.put_frames(SOAPTrajData, lo, hi).reshape(-1, Dc)
         n = int(rows.shape[0])
         dist = th.empty((n, K), dtype=th.float64, device="cuda") if want_dist else None
         amin = th.empty(n, dtype=th.float64, device="cuda")

@@ -22,18 +22,41 @@ __global__ void __launch_bounds__(kTrThreads)
     for (int i = threadIdx.x; i < pairs; i += kTrThreads) hist[i] = 0u;
     __syncthreads();
   }
-  const long long n_steps = (n_frames - window + stride - 1) / stride;  // frames window, window+stride, ...
-  const long long total = n_steps * n_atoms;
-  const long long grid_stride = (long long)gridDim.x * kTrThreads;
-  for (long long i = (long long)blockIdx.x * kTrThreads + threadIdx.x; i < total; i += grid_stride) {
-    const long long step = i / n_atoms, atom = i - step * n_atoms;
-    const long long frame = window + step * stride;
-    const int from = states[(frame - window) * n_atoms + atom], to = states[frame * n_atoms + atom];
-    if ((unsigned)from < (unsigned)n_classes && (unsigned)to < (unsigned)n_classes) {
+  // thread = atom (coalesced rows), blockIdx.y = a slice of the frame steps window, window+stride, ...
+  const long long n_steps = (n_frames - window + stride - 1) / stride;
+  const long long per_y = (n_steps + gridDim.y - 1) / gridDim.y;
+  const long long s0 = (long long)blockIdx.y * per_y, s1 = min(n_steps, s0 + per_y);
+  auto count = [&](int from, int to) {
+    const bool ok = (unsigned)from < (unsigned)n_classes && (unsigned)to < (unsigned)n_classes;
+    // neighbouring atoms mostly make the same transition (few classes, slow dynamics): the lanes of a warp
+    // that hit the same cell elect one of them to add their count (one atomic per distinct cell per warp)
+    const int key = ok ? from * n_classes + to : -1;
+    const unsigned same = __match_any_sync(__activemask(), key);
+    if (ok && (int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) {
       if (use_smem)
-        atomicAdd(&hist[from * n_classes + to], 1u);
+        atomicAdd(&hist[key], (unsigned)__popc(same));
       else
-        atomicAdd(&counts[(size_t)from * n_classes + to], 1ull);
+        atomicAdd(&counts[key], (unsigned long long)__popc(same));
+    }
+  };
+  for (long long atom = (long long)blockIdx.x * kTrThreads + threadIdx.x; atom < n_atoms;
+       atom += (long long)gridDim.x * kTrThreads) {
+    constexpr int kBatch = 4;  // independent loads in flight per thread
+    long long s = s0;
+    for (; s + kBatch <= s1; s += kBatch) {
+      int from[kBatch], to[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const long long frame = window + (s + j) * stride;
+        from[j] = states[(frame - window) * n_atoms + atom];
+        to[j] = states[frame * n_atoms + atom];
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) count(from[j], to[j]);
+    }
+    for (; s < s1; ++s) {
+      const long long frame = window + s * stride;
+      count(states[(frame - window) * n_atoms + atom], states[frame * n_atoms + atom]);
     }
   }
   if (use_smem) {
@@ -68,16 +91,27 @@ __global__ void __launch_bounds__(256)
   long long time = 0;
   int state = states[initial * n_atoms + atom];
   bool first = true;
-  for (long long f = window + initial; f < n_frames; f += window) {
+  auto step = [&](int now) {
     time += window;
-    const int now = states[f * n_atoms + atom];
     if (now != state) {
       emit(state, first ? -time : time);
       first = false;
       state = now;
       time = 0;
     }
+  };
+  // the walk is a dependent chain only through `state`: 8 frames are fetched at once so that a thread
+  // keeps 8 loads in flight (one load per step leaves the memory system ~6 % busy)
+  constexpr int kBatch = 8;
+  long long f = window + initial;
+  for (; f + (kBatch - 1) * window < n_frames; f += kBatch * window) {
+    int nxt[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) nxt[j] = states[(f + j * window) * n_atoms + atom];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) step(nxt[j]);
   }
+  for (; f < n_frames; f += window) step(states[f * n_atoms + atom]);
   emit(state, -time - window);  // the open interval at the end of the series
 }
 
@@ -122,11 +156,14 @@ extern "C" int soap_transition_counts(const int32_t *states, int64_t n_frames, i
   if (window >= n_frames) return SOAP_OK;  // range(window, nframes, stride) is empty
   const int pairs = n_classes * n_classes;
   const size_t smem = pairs <= kTrMaxShared ? (size_t)pairs * 4 : 0;
-  const int64_t total = ((n_frames - window + stride - 1) / stride) * n_atoms;
-  int64_t grid = (total + kTrThreads * 8 - 1) / (kTrThreads * 8);
+  const int64_t n_steps = (n_frames - window + stride - 1) / stride;
+  int64_t gx = (n_atoms + kTrThreads - 1) / kTrThreads;
   const int64_t cap = (int64_t)num_sms() * 8;
-  grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
-  transition_counts_kernel<<<(unsigned)grid, kTrThreads, smem, s>>>(states, n_frames, n_atoms, n_classes, window, stride,
-                                                                    reinterpret_cast<unsigned long long *>(counts));
+  gx = gx > cap ? cap : gx;
+  int64_t gy = (cap + gx - 1) / gx;  // enough CTAs to fill the device; every CTA flushes one histogram
+  gy = gy > n_steps ? n_steps : gy;
+  gy = gy < 1 ? 1 : (gy > 65535 ? 65535 : gy);
+  transition_counts_kernel<<<dim3((unsigned)gx, (unsigned)gy), kTrThreads, smem, s>>>(
+      states, n_frames, n_atoms, n_classes, window, stride, reinterpret_cast<unsigned long long *>(counts));
   return check_launch("transition_counts_kernel");
 }

@@ -50,6 +50,65 @@ class _Uploader:
         self.pinned = [None, None]
         self.busy = [None, None]
         self.turn = 0
+        import os
+
+        self.fill_threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+
+    def _stage(self, k: int, shape, dtype):
+        """pinned staging tensor ``k`` viewed as ``shape`` (waits for the copy that last used it)"""
+        th = self.th
+        n = int(np.prod(shape))
+        if self.busy[k] is not None:
+            self.busy[k].synchronize()
+        if self.pinned[k] is None or self.pinned[k].numel() < n or self.pinned[k].dtype != dtype:
+            self.pinned[k] = th.empty(n, dtype=dtype, pin_memory=True)
+        return self.pinned[k][:n].view(*shape)
+
+    def _launch(self, k: int, stage):
+        th = self.th
+        with th.cuda.stream(self.copy_stream):
+            dev = stage.to("cuda", non_blocking=True)
+            done = th.cuda.Event()
+            done.record(self.copy_stream)
+        self.busy[k] = done
+        th.cuda.current_stream().wait_event(done)
+        dev.record_stream(th.cuda.current_stream())
+        return dev
+
+    def put_frames(self, dataset, lo: int, hi: int):
+        """Frames ``[lo, hi)`` of a chunked dataset -> device tensor, read STRAIGHT into the pinned staging
+        buffer: ``dataset.read_direct`` when the dataset has it (h5py does: no intermediate array), plain
+        slicing otherwise; the frame range is split over a few host threads (numpy releases the GIL while
+        it copies; h5py serialises internally, which is harmless)."""
+        th = self.th
+        dt = np.dtype(getattr(dataset, "dtype", np.float64))
+        if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+            host = np.asarray(dataset[lo:hi]).astype(np.float64)
+            return self.put(host)
+        k = self.turn
+        self.turn ^= 1
+        shape = (hi - lo,) + tuple(int(v) for v in dataset.shape[1:])
+        stage = self._stage(k, shape, th.float32 if dt == np.dtype(np.float32) else th.float64)
+        dst = stage.numpy()
+        direct = getattr(dataset, "read_direct", None)
+
+        def fill(a, b):
+            if direct is not None:
+                direct(dst, np.s_[lo + a : lo + b], np.s_[a:b])
+            else:
+                dst[a:b] = dataset[lo + a : lo + b]
+
+        n = hi - lo
+        parts = max(1, min(self.fill_threads, n))
+        if parts == 1:
+            fill(0, n)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+
+            cuts = [n * i // parts for i in range(parts + 1)]
+            with ThreadPoolExecutor(parts) as pool:
+                list(pool.map(lambda ab: fill(*ab), zip(cuts[:-1], cuts[1:])))
+        return self._launch(k, stage)
 
     def put(self, host: np.ndarray):
         th = self.th
@@ -98,10 +157,7 @@ def stream_time_soap(dataset, settings: dict, windows, euclid: bool = True, kind
     up = _Uploader(th)
     tail = None  # last <= maxw processed frames, on the device
     for lo, hi in frame_ranges(dataset, max_frames):
-        host = np.asarray(dataset[lo:hi])
-        if host.dtype not in (np.float32, np.float64):
-            host = host.astype(np.float64)
-        raw = up.put(host)
+        raw = up.put_frames(dataset, lo, hi)
         h = 0 if tail is None else int(tail.shape[0])
         block = th.empty((h + hi - lo, A, width), dtype=raw.dtype, device="cuda")
         if h:

@@ -26,6 +26,14 @@ class FakeSOAPDataset:
     def __getitem__(self, key):
         return np.array(self._data[key])  # h5py returns a fresh ndarray
 
+    def read_direct(self, dest, source_sel=None, dest_sel=None):
+        """h5py.Dataset.read_direct: read the selection straight into ``dest`` (no intermediate array)"""
+        src = self._data if source_sel is None else self._data[source_sel]
+        if dest_sel is None:
+            np.copyto(dest, src)
+        else:
+            np.copyto(dest[dest_sel], src)
+
     def iter_chunks(self):
         step = self.chunks[0]
         for lo in range(0, self.shape[0], step):

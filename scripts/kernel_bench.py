@@ -148,6 +148,52 @@ def main():
             report("classify(fused)", f"{F}x{A} Dc{Dc} K={K} f64 argmin", ms, F * A * (Dc * 8 + 12), vec_per_s=F * A / ms * 1e3)
             del raw
 
+    # ---- the step after the classification (f4): transition counts and residence times of int[F, A] states
+    if want("transitions"):
+        F, A, K = (500, 20000, 8) if args.quick else (2000, 100000, 8)
+        states = torch.randint(0, K, (F // 20, A), dtype=torch.int32, device="cuda").repeat_interleave(20, dim=0).contiguous()
+        lib = _lib.load()
+        counts = torch.empty((K, K), dtype=torch.int64, device="cuda")
+
+        def events(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        ms = events(lambda: _lib.check(lib.soap_transition_counts(states.data_ptr(), F, A, K, 1, 1, counts.data_ptr(), None)))
+        report("transition_counts", f"{F}x{A} int32 states, {K} classes, window 1", ms, 2 * (F - 1) * A * 4, pairs_per_s=(F - 1) * A / ms * 1e3)
+        cap = int(lib.soap_residence_capacity(F, A, 1, 1))
+        ev_s = torch.empty(cap, dtype=torch.int32, device="cuda")
+        ev_t = torch.empty(cap, dtype=torch.int64, device="cuda")
+        n_ev = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ms = events(lambda: _lib.check(lib.soap_residence_events(states.data_ptr(), F, A, K, 1, 1, ev_s.data_ptr(), ev_t.data_ptr(), cap,
+                                                                 n_ev.data_ptr(), None)))
+        report("residence_events", f"{F}x{A} int32 states, window 1 ({int(n_ev.item())} events)", ms, F * A * 4 + int(n_ev.item()) * 12,
+               states_per_s=F * A / ms * 1e3)
+        del states, ev_s, ev_t
+
+    # ---- chunked dataset -> pinned ring -> HBM -> kernels (f2): getTimeSOAPSimple on an HDF5-like dataset
+    if want("stream"):
+        import time
+        from oracle.fake_dataset import FakeSOAPDataset, dscribe_attrs
+        F, A = (200, 2000) if args.quick else (400, 5000)
+        attrs, dc = dscribe_attrs(8, 8, ["H", "O"])
+        host = np.random.default_rng(1).random((F, A, dc))
+        ds = FakeSOAPDataset(host, 100, attrs)
+        S.getTimeSOAPSimple(ds)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        S.getTimeSOAPSimple(ds)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        report("getTimeSOAPSimple(stream)", f"{F}x{A}x{dc} f64 pageable numpy chunks of 100 frames -> host results", ms, host.nbytes,
+               note="wall clock incl. chunk read, pinned staging, H2D, expand+normalise, timelag, D2H")
+        del host, ds
+
     # ---- pair kernels (all-pairs matrix, configs[3]: D = 576)
     if want("pairs"):
         N = 8192 if args.quick else 25000
