@@ -24,3 +24,7 @@ ts = timelag_device(dev, W, _lib.KIND_SIMPLE, 1, mult=mult)
 print("kernels (timelag + 4 diff): %.1f ms" % tm(lambda: [diff_transposed_device(t) for t in timelag_device(dev, W, _lib.KIND_SIMPLE, 1, mult=mult)]))
 dts = [diff_transposed_device(t) for t in ts]
 print("D2H results .cpu(): %.1f ms" % tm(lambda: [(t.cpu(), d.cpu()) for t, d in zip(ts, dts)]))
+arr = host.numpy().copy()  # pageable numpy: what a user gets from h5py
+t0 = time.perf_counter(); r = S.timeSOAPfromCompressed(arr, 8, 8, ["H", "O"], slices, windows=W); sync(); t1 = time.perf_counter()
+t2 = time.perf_counter(); r = S.timeSOAPfromCompressed(arr, 8, 8, ["H", "O"], slices, windows=W); sync(); t3 = time.perf_counter()
+print("full API call, pageable numpy in -> numpy out: first %.1f ms, second %.1f ms (%.1f GB/s)" % ((t1 - t0) * 1e3, (t3 - t2) * 1e3, arr.nbytes / (t3 - t2) / 1e9))

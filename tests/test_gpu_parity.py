@@ -356,6 +356,37 @@ def test_pinned_host_tensor_is_uploaded_in_overlapped_atom_tiles(S, monkeypatch)
     assert_array_equal(t2.numpy(), S.timeSOAPfromCompressed(raw, 8, 8, windows=(5,), **kw)[0][0])
 
 
+def test_large_pageable_arrays_are_staged_in_pieces(S, monkeypatch):
+    """numpy / pageable tensors above 64 MB go to HBM through two fixed pinned buffers (no whole-array pin)."""
+    import torch
+    from cpctools_b200 import _device
+
+    monkeypatch.setattr(_device._HostStager, "MIN_BYTES", 1 << 16)
+    monkeypatch.setattr(_device._HostStager, "CHUNK", (1 << 20) + 24)  # several pieces, a ragged last one
+    monkeypatch.setattr(_device, "_stager", None)
+    rng = np.random.default_rng(5)
+    for arr in (rng.random((37, 11, 1224)), rng.random((3, 70001)).astype(np.float32), rng.integers(0, 9, (5, 40001))):
+        dev = _device.to_device(arr)
+        assert dev.is_cuda and tuple(dev.shape) == arr.shape
+        assert_array_equal(dev.cpu().numpy(), arr)
+        ro = arr.copy()
+        ro.setflags(write=False)
+        assert_array_equal(_device.to_device(ro).cpu().numpy(), arr)
+    t = torch.from_numpy(rng.random((64, 4099)))
+    assert_array_equal(_device.to_device(t).cpu().numpy(), t.numpy())
+    attrs, dc = dscribe_attrs(8, 8, ["H", "O"])
+    kw = dict(atomTypes=["H", "O"], atomicSlices=_slices_from_attrs(attrs))
+    raw = synthetic_soap((40, 9, dc), seed=2, kind="W")
+    monkeypatch.setattr(_device, "_stager", None)
+    got = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1, 5), **kw)
+    monkeypatch.setattr(_device._HostStager, "MIN_BYTES", 1 << 40)
+    want = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1, 5), **kw)
+    for (t1, d1), (t2, d2) in zip(got, want):
+        assert_array_equal(t1, t2)
+        assert_array_equal(d1, d2)
+    monkeypatch.setattr(_device, "_stager", None)
+
+
 def test_config1_shape_against_the_loop_oracle(S):
     """BASELINE configs[0]: 309 atoms x 200 frames, 1 species (Dc 324 -> Df 576), fp64, the reference's
     own Python-loop path (oracle port) as the checker, default distance and SOAPdistanceNormalized."""
