@@ -95,6 +95,55 @@ class _HostStager:
         return dev
 
 
+    def download(self, t) -> np.ndarray:
+        """HBM -> fresh pageable numpy array, the mirror image of :meth:`upload` (a plain ``.cpu()`` into
+        untouched pageable memory runs at a fraction of the link rate: one thread takes all the page faults)."""
+        th = torch
+        t = t.detach().contiguous()
+        out = np.empty(tuple(t.shape), dtype=th.empty(0, dtype=t.dtype).numpy().dtype)
+        flat = out.reshape(-1).view(np.uint8)
+        src = t.reshape(-1).view(th.uint8)
+        n = int(flat.size)
+        with self.lock:
+            if self.stream is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self.stream = th.cuda.Stream()
+                self.pool = ThreadPoolExecutor(self.threads)
+            self.stream.wait_stream(th.cuda.current_stream())
+            for k in range(2):
+                if self.bufs[k] is None:
+                    self.bufs[k] = th.empty(self.CHUNK, dtype=th.uint8, pin_memory=True)
+                if self.events[k] is not None:
+                    self.events[k].synchronize()
+                    self.events[k] = None
+            offs = list(range(0, n, self.CHUNK))
+            done = [None, None]
+
+            def fetch(i):
+                off = offs[i]
+                m = min(self.CHUNK, n - off)
+                with th.cuda.stream(self.stream):
+                    self.bufs[i & 1][:m].copy_(src[off : off + m], non_blocking=True)
+                    ev = th.cuda.Event()
+                    ev.record(self.stream)
+                done[i & 1] = ev
+
+            if offs:
+                fetch(0)
+            for i, off in enumerate(offs):
+                m = min(self.CHUNK, n - off)
+                done[i & 1].synchronize()
+                if i + 1 < len(offs):
+                    fetch(i + 1)  # the other pinned buffer: its previous contents were drained last iteration
+                buf = self.bufs[i & 1].numpy()
+                cuts = [m * j // self.threads for j in range(self.threads + 1)]
+                list(self.pool.map(lambda ab: np.copyto(flat[off + ab[0] : off + ab[1]], buf[ab[0] : ab[1]]),
+                                   zip(cuts[:-1], cuts[1:])))
+            src.record_stream(self.stream)
+        return out
+
+
 _stager = None
 
 
@@ -140,6 +189,12 @@ def to_device(x, dtype=None):
 
 
 def to_host(t) -> np.ndarray:
+    global _stager
+    if t.is_cuda and t.numel() * t.element_size() >= _HostStager.MIN_BYTES and t.dtype in (
+            torch.float32, torch.float64, torch.int32, torch.int64):
+        if _stager is None:
+            _stager = _HostStager()
+        return _stager.download(t)
     return t.detach().cpu().numpy()
 
 

@@ -28,3 +28,12 @@ arr = host.numpy().copy()  # pageable numpy: what a user gets from h5py
 t0 = time.perf_counter(); r = S.timeSOAPfromCompressed(arr, 8, 8, ["H", "O"], slices, windows=W); sync(); t1 = time.perf_counter()
 t2 = time.perf_counter(); r = S.timeSOAPfromCompressed(arr, 8, 8, ["H", "O"], slices, windows=W); sync(); t3 = time.perf_counter()
 print("full API call, pageable numpy in -> numpy out: first %.1f ms, second %.1f ms (%.1f GB/s)" % ((t1 - t0) * 1e3, (t3 - t2) * 1e3, arr.nbytes / (t3 - t2) / 1e9))
+# expansion with numpy in / numpy out (the reference's container): 2.45 GB in, 3.46 GB out
+x = arr[:200]
+for rep in range(2):
+    t0 = time.perf_counter(); y = S.fillSOAPVectorFromdscribe(x, 8, 8, ["H", "O"], slices); t1 = time.perf_counter()
+    print("fillSOAPVectorFromdscribe numpy->numpy %s -> %s: %.1f ms (%.1f GB/s of in+out)" % (x.shape, y.shape, (t1 - t0) * 1e3, (x.nbytes + y.nbytes) / (t1 - t0) / 1e9))
+_device._HostStager.MIN_BYTES = 1 << 50  # the plain paths: whole-array pin for the upload, .cpu() for the download
+for rep in range(2):
+    t0 = time.perf_counter(); y = S.fillSOAPVectorFromdscribe(x, 8, 8, ["H", "O"], slices); t1 = time.perf_counter()
+    print("  same without staging: %.1f ms (%.1f GB/s)" % ((t1 - t0) * 1e3, (x.nbytes + y.nbytes) / (t1 - t0) / 1e9))

@@ -374,6 +374,13 @@ def test_large_pageable_arrays_are_staged_in_pieces(S, monkeypatch):
         assert_array_equal(_device.to_device(ro).cpu().numpy(), arr)
     t = torch.from_numpy(rng.random((64, 4099)))
     assert_array_equal(_device.to_device(t).cpu().numpy(), t.numpy())
+    for shape, dt in (((37, 11, 1224), torch.float64), ((3, 70001), torch.float32), ((7, 30011), torch.int32)):
+        d = (torch.rand(shape, device="cuda") * 100).to(dt)
+        back = _device.to_host(d)  # staged download, several ragged pieces
+        assert back.shape == shape and back.flags.writeable
+        assert_array_equal(back, d.cpu().numpy())
+    nc = torch.rand(5, 40000, device="cuda", dtype=torch.float64).T  # non-contiguous source
+    assert_array_equal(_device.to_host(nc), nc.cpu().numpy())
     attrs, dc = dscribe_attrs(8, 8, ["H", "O"])
     kw = dict(atomTypes=["H", "O"], atomicSlices=_slices_from_attrs(attrs))
     raw = synthetic_soap((40, 9, dc), seed=2, kind="W")
