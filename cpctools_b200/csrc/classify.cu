@@ -110,7 +110,10 @@ constexpr int kCtWarps = 8;
 constexpr int kCtThreads = (kCtWarps + 3) * 32;  // + TMA producer warp + two finisher warps (alternating tiles)
 constexpr int kCtMaxK = 32;
 
-template <typename T, int KMAX>
+// VPL = vectors per lane: a tile holds 32 * VPL vectors and lane l owns vectors l, l + 32, ...  One broadcast
+// load of the references / multiplicities then serves VPL vectors, which takes the kernel off the
+// shared-memory roofline for small dictionaries (K <= 8: 13 -> 8.5 wavefronts per vector unit).
+template <typename T, int KMAX, int VPL>
 __global__ void __launch_bounds__(kCtThreads, 1)
     classify_tiled_kernel(const T *__restrict__ X, const double *__restrict__ mult, const double *__restrict__ refw,
                           const double *__restrict__ ref_norm2, long long nvec, int D, int K, int kind, int power,
@@ -121,11 +124,12 @@ __global__ void __launch_bounds__(kCtThreads, 1)
   constexpr int UE = 16 / (int)sizeof(T);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Dp = npieces * upp * UE;                   // padded dimension (multiple of the unit)
-  unsigned char *stage0 = smem_ct;                     // [nstage][32 slots][stride]
-  double *sm_m = reinterpret_cast<double *>(smem_ct + (size_t)nstage * 32 * stride);  // [Dp]
+  constexpr int TV = 32 * VPL;                          // vectors per tile
+  unsigned char *stage0 = smem_ct;                     // [nstage][TV slots][stride]
+  double *sm_m = reinterpret_cast<double *>(smem_ct + (size_t)nstage * TV * stride);  // [Dp]
   double *sm_r = sm_m + Dp;                            // [K][Dp]
-  double *red = sm_r + (size_t)K * Dp;                 // [2][kCtWarps][K+1][32]
-  const size_t red_elems = (size_t)kCtWarps * (K + 1) * 32;
+  double *red = sm_r + (size_t)K * Dp;                 // [2][kCtWarps][K+1][TV]
+  const size_t red_elems = (size_t)kCtWarps * (K + 1) * TV;
   uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * red_elems);  // [nstage]
   uint64_t *empty = full + nstage, *red_full = empty + nstage, *red_empty = red_full + 2;
 
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(kCtThreads, 1)
   }
   __syncthreads();
 
-  const long long ntiles = (nvec + 31) / 32;
+  const long long ntiles = (nvec + TV - 1) / TV;
   const long long my_first = blockIdx.x;
   if (warp == kCtWarps) {
     // ===== producer: ONE tensor-map box (32 vectors x one piece) per stage ==========================
@@ -158,8 +162,8 @@ __global__ void __launch_bounds__(kCtThreads, 1)
       for (int p = 0; p < npieces; ++p, ++it) {
         if (it >= nstage) mbar_wait(&empty[s], (uint32_t)(ph ^ 1));
         if (lane == 0) {
-          mbar_expect_tx(&full[s], 32u * (uint32_t)stride);
-          tma_load_2d(stage0 + (size_t)s * 32 * stride, &tmap, p * (stride / 8), (int)(t * 32), &full[s]);
+          mbar_expect_tx(&full[s], (uint32_t)TV * (uint32_t)stride);
+          tma_load_2d(stage0 + (size_t)s * TV * stride, &tmap, p * (stride / 8), (int)(t * TV), &full[s]);
         }
         if (++s == nstage) s = 0, ph ^= 1;
       }
@@ -174,36 +178,40 @@ __global__ void __launch_bounds__(kCtThreads, 1)
       const int rb = (int)(tcount & 1);
       mbar_wait(&red_full[rb], (uint32_t)((tcount >> 1) & 1));
       const double *r = red + rb * red_elems;
-      const long long v = t * 32 + lane;
-      double uu = 0.0;
-      for (int w = 0; w < kCtWarps; ++w) uu += r[((size_t)w * (K + 1)) * 32 + lane];
-      double best_v = 0.0;
-      int best_j = -1;
-      const double nu = (kind == SOAP_KIND_NORMALIZED && normalize_x) ? ((uu == 0.0) ? 1.0 : sqrt(uu)) : 1.0;
-      double d[KMAX];
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {  // independent chains: the compiler interleaves them
-        if (k < K) {
-          double uv = 0.0;
+      for (int vi = 0; vi < VPL; ++vi) {
+        const int vl = vi * 32 + lane;
+        const long long v = t * TV + vl;
+        double uu = 0.0;
+        for (int w = 0; w < kCtWarps; ++w) uu += r[((size_t)w * (K + 1)) * TV + vl];
+        double best_v = 0.0;
+        int best_j = -1;
+        const double nu = (kind == SOAP_KIND_NORMALIZED && normalize_x) ? ((uu == 0.0) ? 1.0 : sqrt(uu)) : 1.0;
+        double d[KMAX];
 #pragma unroll
-          for (int w = 0; w < kCtWarps; ++w) uv += r[((size_t)w * (K + 1) + k + 1) * 32 + lane];
-          d[k] = (kind == SOAP_KIND_NORMALIZED) ? sqrt(fabs(2.0 - 2.0 * (uv / nu)))
-                                                : soap_epilogue(uv, uu, ref_norm2[k], kind, power);
+        for (int k = 0; k < KMAX; ++k) {  // independent chains: the compiler interleaves them
+          if (k < K) {
+            double uv = 0.0;
+#pragma unroll
+            for (int w = 0; w < kCtWarps; ++w) uv += r[((size_t)w * (K + 1) + k + 1) * TV + vl];
+            d[k] = (kind == SOAP_KIND_NORMALIZED) ? sqrt(fabs(2.0 - 2.0 * (uv / nu)))
+                                                  : soap_epilogue(uv, uu, ref_norm2[k], kind, power);
+          }
         }
-      }
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k < K) {
-          if (v < nvec && dist_out) dist_out[(size_t)v * K + k] = d[k];
-          if (best_j < 0 || cls_better(d[k], k, best_v, best_j)) { best_v = d[k]; best_j = k; }
+        for (int k = 0; k < KMAX; ++k) {
+          if (k < K) {
+            if (v < nvec && dist_out) dist_out[(size_t)v * K + k] = d[k];
+            if (best_j < 0 || cls_better(d[k], k, best_v, best_j)) { best_v = d[k]; best_j = k; }
+          }
+        }
+        if (v < nvec) {
+          if (argmin_out) argmin_out[v] = best_j;
+          if (min_out) min_out[v] = best_v;
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&red_empty[rb]);
-      if (v < nvec) {
-        if (argmin_out) argmin_out[v] = best_j;
-        if (min_out) min_out[v] = best_v;
-      }
     }
   } else {
     // ===== consumers ================================================================================
@@ -211,40 +219,55 @@ __global__ void __launch_bounds__(kCtThreads, 1)
     long long tcount = 0;
     int s = 0, ph = 0;
     for (long long t = my_first; t < ntiles; t += gridDim.x) {
-      double acc[KMAX + 1];  // statically indexed everywhere: stays in registers
+      double acc[VPL][KMAX + 1];  // statically indexed everywhere: stays in registers
 #pragma unroll
-      for (int q = 0; q <= KMAX; ++q) acc[q] = 0.0;
+      for (int vi = 0; vi < VPL; ++vi)
+#pragma unroll
+        for (int q = 0; q <= KMAX; ++q) acc[vi][q] = 0.0;
       for (int p = 0; p < npieces; ++p) {
         const int e0 = p * upp * UE;
         const int punits = (min(D - e0, upp * UE) + UE - 1) / UE;
         mbar_wait(&full[s], (uint32_t)ph);
-        const uint32_t xrow = st_addr + (uint32_t)((s * 32 + lane) * stride);
+        const uint32_t xrow = st_addr + (uint32_t)((s * TV + lane) * stride);  // vector vi of this lane: + vi * 32 slots
         for (int u = warp; u < punits; u += kCtWarps) {
-          double x0, x1;
           if constexpr (sizeof(T) == 8) {
-            const double2 xv = lds_d2(xrow + 16u * u);
-            x0 = xv.x; x1 = xv.y;
+            double2 xv[VPL];
+#pragma unroll
+            for (int vi = 0; vi < VPL; ++vi) xv[vi] = lds_d2(xrow + (uint32_t)(vi * 32) * (uint32_t)stride + 16u * u);
             const uint32_t eo = (uint32_t)(e0 + 2 * u) * 8u;
             const double2 mv = lds_d2(m_addr + eo);
-            acc[0] = fma(x0 * mv.x, x0, acc[0]);
-            acc[0] = fma(x1 * mv.y, x1, acc[0]);
+#pragma unroll
+            for (int vi = 0; vi < VPL; ++vi) {
+              acc[vi][0] = fma(xv[vi].x * mv.x, xv[vi].x, acc[vi][0]);
+              acc[vi][0] = fma(xv[vi].y * mv.y, xv[vi].y, acc[vi][0]);
+            }
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
               if (k < K) {
                 const double2 rv = lds_d2(r_addr + (uint32_t)k * (uint32_t)Dp * 8u + eo);
-                acc[k + 1] = fma(x0, rv.x, acc[k + 1]);
-                acc[k + 1] = fma(x1, rv.y, acc[k + 1]);
+#pragma unroll
+                for (int vi = 0; vi < VPL; ++vi) {
+                  acc[vi][k + 1] = fma(xv[vi].x, rv.x, acc[vi][k + 1]);
+                  acc[vi][k + 1] = fma(xv[vi].y, rv.y, acc[vi][k + 1]);
+                }
               }
             }
           } else {
-            const float4 xv = lds_f4(xrow + 16u * u);
-            const double xs[4] = {(double)xv.x, (double)xv.y, (double)xv.z, (double)xv.w};
+            double xs[VPL][4];
+#pragma unroll
+            for (int vi = 0; vi < VPL; ++vi) {
+              const float4 xv = lds_f4(xrow + (uint32_t)(vi * 32) * (uint32_t)stride + 16u * u);
+              xs[vi][0] = (double)xv.x; xs[vi][1] = (double)xv.y; xs[vi][2] = (double)xv.z; xs[vi][3] = (double)xv.w;
+            }
             const uint32_t eo = (uint32_t)(e0 + 4 * u) * 8u;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const double2 mv = lds_d2(m_addr + eo + 16u * h);
-              acc[0] = fma(xs[2 * h] * mv.x, xs[2 * h], acc[0]);
-              acc[0] = fma(xs[2 * h + 1] * mv.y, xs[2 * h + 1], acc[0]);
+#pragma unroll
+              for (int vi = 0; vi < VPL; ++vi) {
+                acc[vi][0] = fma(xs[vi][2 * h] * mv.x, xs[vi][2 * h], acc[vi][0]);
+                acc[vi][0] = fma(xs[vi][2 * h + 1] * mv.y, xs[vi][2 * h + 1], acc[vi][0]);
+              }
             }
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
@@ -252,8 +275,11 @@ __global__ void __launch_bounds__(kCtThreads, 1)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                   const double2 rv = lds_d2(r_addr + (uint32_t)k * (uint32_t)Dp * 8u + eo + 16u * h);
-                  acc[k + 1] = fma(xs[2 * h], rv.x, acc[k + 1]);
-                  acc[k + 1] = fma(xs[2 * h + 1], rv.y, acc[k + 1]);
+#pragma unroll
+                  for (int vi = 0; vi < VPL; ++vi) {
+                    acc[vi][k + 1] = fma(xs[vi][2 * h], rv.x, acc[vi][k + 1]);
+                    acc[vi][k + 1] = fma(xs[vi][2 * h + 1], rv.y, acc[vi][k + 1]);
+                  }
                 }
               }
             }
@@ -268,8 +294,10 @@ __global__ void __launch_bounds__(kCtThreads, 1)
       if (tcount >= 2) mbar_wait(&red_empty[rb], (uint32_t)(((tcount >> 1) - 1) & 1));
       double *r = red + rb * red_elems;
 #pragma unroll
-      for (int q = 0; q <= KMAX; ++q)
-        if (q <= K) r[((size_t)warp * (K + 1) + q) * 32 + lane] = acc[q];
+      for (int vi = 0; vi < VPL; ++vi)
+#pragma unroll
+        for (int q = 0; q <= KMAX; ++q)
+          if (q <= K) r[((size_t)warp * (K + 1) + q) * TV + vi * 32 + lane] = acc[vi][q];
       __syncwarp();
       if (lane == 0) mbar_arrive(&red_full[rb]);
       ++tcount;
@@ -300,46 +328,58 @@ extern "C" int soap_classify(const void *X, const void *mult, const double *refw
     const size_t budget = (size_t)max_smem_optin() - 2048;
     if (aligned && n_refs <= kCtMaxK && (dtype == SOAP_F64 || dtype == SOAP_F32)) {
       // pieces of an odd number of 16-byte units (slots 16*odd bytes apart, <= 127 units = one box row);
-      // as many stages as fit, preferring >= 64 KB in flight per SM and then the fewest pieces
-      int best_upp = 0, best_pieces = 0, best_stage = 0;
-      size_t best_score = 0;
-      for (int npieces = 1; npieces <= n_units; ++npieces) {
-        const int upp = ((n_units + npieces - 1) / npieces) | 1;
-        if (upp > 127 || upp > n_units) continue;
-        const int real_pieces = (n_units + upp - 1) / upp;
-        const size_t Dp = (size_t)real_pieces * upp * ue;
-        const size_t fixed = (size_t)(n_refs + 1) * Dp * 8 + (size_t)2 * kCtWarps * (n_refs + 1) * 32 * 8 + 256;
-        for (int st = 4; st >= 2; --st) {
-          if ((size_t)st * 32 * 16 * upp + fixed > budget) continue;
-          size_t score = (size_t)(st - 1) * 32 * 16 * upp;
-          if (score > 65536) score = 65536;
-          if (score > best_score) best_score = score, best_upp = upp, best_pieces = real_pieces, best_stage = st;
-          break;
+      // as many stages as fit, preferring >= 64 KB in flight per SM and then the fewest pieces.  Small
+      // dictionaries take two vectors per lane (64-vector tiles) when that still leaves >= 48 KB in flight.
+      auto plan = [&](int vpl, int &o_upp, int &o_pieces, int &o_stage) -> size_t {
+        size_t best_score = 0;
+        o_upp = 0;
+        for (int npieces = 1; npieces <= n_units; ++npieces) {
+          const int upp = ((n_units + npieces - 1) / npieces) | 1;
+          if (upp > 127 || upp > n_units) continue;
+          const int real_pieces = (n_units + upp - 1) / upp;
+          const size_t Dp = (size_t)real_pieces * upp * ue;
+          const size_t fixed = (size_t)(n_refs + 1) * Dp * 8 + (size_t)2 * kCtWarps * (n_refs + 1) * 32 * vpl * 8 + 256;
+          for (int st = 4; st >= 2; --st) {
+            if ((size_t)st * 32 * vpl * 16 * upp + fixed > budget) continue;
+            size_t score = (size_t)(st - 1) * 32 * vpl * 16 * upp;
+            if (score > 65536) score = 65536;
+            if (score > best_score) best_score = score, o_upp = upp, o_pieces = real_pieces, o_stage = st;
+            break;
+          }
         }
+        return best_score;
+      };
+      int vpl = 1, best_upp = 0, best_pieces = 0, best_stage = 0;
+      if (n_refs <= 8) {
+        int u2, p2, s2;
+        if (plan(2, u2, p2, s2) >= 49152) vpl = 2, best_upp = u2, best_pieces = p2, best_stage = s2;
       }
+      if (vpl == 1) plan(1, best_upp, best_pieces, best_stage);
       if (best_upp > 0) {
-        const int upp = best_upp, real_pieces = best_pieces, stride = 16 * best_upp, nstage = best_stage;
+        const int upp = best_upp, real_pieces = best_pieces, stride = 16 * best_upp, nstage = best_stage, tv = 32 * vpl;
         const size_t Dp = (size_t)real_pieces * upp * ue;
-        const size_t smem_t = (size_t)nstage * 32 * stride + (size_t)(n_refs + 1) * Dp * 8 +
-                              (size_t)2 * kCtWarps * (n_refs + 1) * 32 * 8 + 256;
-        const long long ntiles = (nvec + 31) / 32;
+        const size_t smem_t = (size_t)nstage * tv * stride + (size_t)(n_refs + 1) * Dp * 8 +
+                              (size_t)2 * kCtWarps * (n_refs + 1) * tv * 8 + 256;
+        const long long ntiles = (nvec + tv - 1) / tv;
         const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
         CUtensorMap tmap;
-        int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, nvec, (int64_t)dim * es / 8, stride / 8, 32,
+        int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, nvec, (int64_t)dim * es / 8, stride / 8, tv,
                                     CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
         ProfScope prof(SOAP_PROF_PAIRS, s);
-#define CT_LAUNCH(T, KM)                                                                                              \
+#define CT_LAUNCH(T, KM, VP)                                                                                          \
   do {                                                                                                                \
-    SOAP_CUDA(cudaFuncSetAttribute(classify_tiled_kernel<T, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-    classify_tiled_kernel<T, KM><<<grid, kCtThreads, smem_t, s>>>(                                                    \
+    SOAP_CUDA(cudaFuncSetAttribute(classify_tiled_kernel<T, KM, VP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+    classify_tiled_kernel<T, KM, VP><<<grid, kCtThreads, smem_t, s>>>(                                                \
         static_cast<const T *>(X), static_cast<const double *>(mult), refw, ref_norm2, nvec, dim, n_refs, kind, power, \
-        normalize_x, dist_out, argmin_out, min_out, upp, real_pieces, stride, nstage, tmap);                                        \
+        normalize_x, dist_out, argmin_out, min_out, upp, real_pieces, stride, nstage, tmap);                          \
   } while (0)
         if (dtype == SOAP_F64) {
-          if (n_refs <= 8) CT_LAUNCH(double, 8); else if (n_refs <= 16) CT_LAUNCH(double, 16); else CT_LAUNCH(double, 32);
+          if (n_refs <= 8) { if (vpl == 2) CT_LAUNCH(double, 8, 2); else CT_LAUNCH(double, 8, 1); }
+          else if (n_refs <= 16) CT_LAUNCH(double, 16, 1); else CT_LAUNCH(double, 32, 1);
         } else {
-          if (n_refs <= 8) CT_LAUNCH(float, 8); else if (n_refs <= 16) CT_LAUNCH(float, 16); else CT_LAUNCH(float, 32);
+          if (n_refs <= 8) { if (vpl == 2) CT_LAUNCH(float, 8, 2); else CT_LAUNCH(float, 8, 1); }
+          else if (n_refs <= 16) CT_LAUNCH(float, 16, 1); else CT_LAUNCH(float, 32, 1);
         }
 #undef CT_LAUNCH
         return check_launch("classify_tiled_kernel");
