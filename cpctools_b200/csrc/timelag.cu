@@ -404,19 +404,32 @@ __global__ void __launch_bounds__(256)
     const long long a = a0 + al, f = f0 + lx;
     if (a < A && f < F) {
       const double *base = scratch + (size_t)a * split * Q * (size_t)F;
-      double uu = 0.0;
-      for (int p = 0; p < split; ++p) uu += base[((size_t)p * Q) * F + f];
+      // all loads of a thread are independent: issued before the (fixed-order) sums so that a thread keeps
+      // Q + NW of them in flight per piece instead of one
+      double uu = 0.0, uv[NW], vv[NW];
 #pragma unroll
-      for (int k = 0; k < NW; ++k) {
-        if (f >= win[k]) {
-          double uv = 0.0, vv = 0.0;
-          for (int p = 0; p < split; ++p) {
-            uv += base[((size_t)p * Q + 1 + k) * F + f];
-            vv += base[((size_t)p * Q) * F + (f - win[k])];
-          }
-          tile[k][lx][al] = soap_epilogue(uv, uu, vv, kind, power);
+      for (int k = 0; k < NW; ++k) uv[k] = vv[k] = 0.0;
+#pragma unroll 2
+      for (int p = 0; p < split; ++p) {
+        const double *bp = base + ((size_t)p * Q) * F;
+        const double u = bp[f];
+        double a[NW], b[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          const bool on = f >= win[k];
+          a[k] = on ? bp[(size_t)(1 + k) * F + f] : 0.0;
+          b[k] = on ? bp[f - win[k]] : 0.0;
+        }
+        uu += u;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+          uv[k] += a[k];
+          vv[k] += b[k];
         }
       }
+#pragma unroll
+      for (int k = 0; k < NW; ++k)
+        if (f >= win[k]) tile[k][lx][al] = soap_epilogue(uv[k], uu, vv[k], kind, power);
     }
   }
   __syncthreads();
