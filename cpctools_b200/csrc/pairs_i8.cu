@@ -26,6 +26,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 namespace soapb {
@@ -64,6 +65,19 @@ __device__ __forceinline__ double fast_cosine_distance(double g, double rr, int 
     return sqrt(2.0 - 2.0 * (1.0 - cosd));
   }
   return sqrt(2.0 - 2.0 * ipow(c, power));
+}
+
+// fp32 outputs: the exact dot (one fp32 rounding) is normalised in double and 2 - 2k formed with one DFMA
+// (the cancellation for k ~ 1 happens in double); clip and square root run in fp32.  For SIMPLE,
+// 2 - 2 (1 - clip(1 - c, 0, 2)) == clip(2 - 2c, 0, 4) up to 1e-16; a negative KERNEL argument gives NaN
+// like numpy's sqrt.
+__device__ __forceinline__ float cosine_distance_f32(float g, double rr, int kind, int power) {
+  const double c = (double)g * rr;
+  float d2 = (float)fma(-2.0, kind == SOAP_KIND_SIMPLE ? c : ipow(c, power), 2.0);
+  if (kind == SOAP_KIND_SIMPLE) d2 = (d2 != d2) ? d2 : fminf(fmaxf(d2, 0.0f), 4.0f);
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(d2));
+  return r;
 }
 
 // ---- pre-pass: row scale, digit planes (zero padded to Dp), squared row norms ----------------------
@@ -328,74 +342,17 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
         const uint32_t taddr = tmem_base + (uint32_t)(as * ND * BN) + ((uint32_t)(q * 32) << 16);
         if constexpr (ND == 3) {
           const bool vec4 = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-          if (lean) {
-            const float prow = __int_as_float((ei - 1023 + 127) << 23);
-#pragma unroll 1
-            for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 16); c += PARTS) {
-              uint32_t v[ND][16];
-#pragma unroll
-              for (int g = 0; g < ND; ++g) tmem_ld16(taddr + (uint32_t)(g * BN + c * 16), v[g]);
-              float cj[16];
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 c4 = *reinterpret_cast<const float4 *>(my_exp + c * 16 + j);
-                cj[j] = c4.x; cj[j + 1] = c4.y; cj[j + 2] = c4.z; cj[j + 3] = c4.w;
-              }
-              tmem_ld_wait();
-              const long long col0 = (long long)tn * BN + c * 16;
-              // a lane owns a ROW of the accumulator: storing from registers sends 32 requests of 16 bytes per
-              // instruction to L2, one per clock (measured: 0.55 of 2.1 ms exposed).  The chunk goes through a
-              // padded shared-memory tile instead and leaves as 64 contiguous bytes per row (4 lanes each).
-              // (A TMA tile store of the same chunk measured slower: the proxy fence sits on the critical path.)
-              float *stg = reinterpret_cast<float *>(epi_stage + (warp - 2) * (32 * kI8StagePitch));
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                float o[4];
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                  const int jj = j + k4;
-                  const float tf = fmaf(fmaf((float)(int)v[2][jj], 1.0f / 256.0f, (float)(int)v[1][jj]), 1.0f / 256.0f,
-                                        (float)(int)v[0][jj]);
-                  // 2 - 2 g with g = tf * 2^(e_i + e_j): the scaling is exact, so this is the general path's value
-                  asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(prow * cj[jj], tf, 2.0f))));
-                }
-                *reinterpret_cast<float4 *>(stg + lane * (kI8StagePitch / 4) + j) = make_float4(o[0], o[1], o[2], o[3]);
-                if (symmetric && row_ok) {  // out[col][row]: the 32 lanes of a warp write 32 consecutive rows
-#pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4)
-                    if (col0 + j + k4 < N) reinterpret_cast<float *>(out)[(size_t)(col0 + j + k4) * ldo + row] = o[k4];
-                }
-              }
-              __syncwarp();
-              if (!(debug_flags & 4)) {
-                const int cq = (lane & 3) * 4;
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                  const int r = 8 * m + (lane >> 2);
-                  const long long grow = (long long)tm * BM + q * 32 + r;
-                  const float4 val = *reinterpret_cast<const float4 *>(stg + r * (kI8StagePitch / 4) + cq);
-                  if (grow < M) {
-                    float *dst = reinterpret_cast<float *>(out) + (size_t)grow * ldo + col0 + cq;
-                    if (vec4 && col0 + cq + 4 <= N) {
-                      *reinterpret_cast<float4 *>(dst) = val;
-                    } else {
-                      if (col0 + cq + 0 < N) dst[0] = val.x;
-                      if (col0 + cq + 1 < N) dst[1] = val.y;
-                      if (col0 + cq + 2 < N) dst[2] = val.z;
-                      if (col0 + cq + 3 < N) dst[3] = val.w;
-                    }
-                  }
-                }
-              }
-              __syncwarp();
-            }
-          } else
+          const float prow = __int_as_float((min(max(ei - 1023, -126), 127) + 127) << 23);  // used when `lean`
+          // one chunk loop, three compile-time flavours of the per-output arithmetic:
+          // 0 = lean SOAPdistanceNormalized, 1 = general SOAPdistanceNormalized, 2 = cosine kinds
+          auto chunk_loop = [&](auto mode_tag) {
+          constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll 1
           for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 16); c += PARTS) {
             uint32_t v[ND][16];
 #pragma unroll
             for (int g = 0; g < ND; ++g) tmem_ld16(taddr + (uint32_t)(g * BN + c * 16), v[g]);
-            int ej[16];
+            int ej[16];  // lean: the bits of c_j = -2 * 2^(e_j - 1023) as floats; otherwise biased exponents
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const int4 e4 = *reinterpret_cast<const int4 *>(my_exp + c * 16 + j);
@@ -403,7 +360,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
             }
             tmem_ld_wait();
             const long long col0 = (long long)tn * BN + c * 16;
-            float *dst = reinterpret_cast<float *>(out) + (size_t)row * ldo + col0;
+            // a lane owns a ROW of the accumulator: storing from registers sends 32 requests of 16 bytes per
+            // instruction to L2, one per clock (measured: 0.55 of 2.1 ms exposed).  The chunk goes through a
+            // padded shared-memory tile instead and leaves as 64 contiguous bytes per row (4 lanes each).
+            // (A TMA tile store of the same chunk measured slower: the proxy fence sits on the critical path.)
+            float *stg = reinterpret_cast<float *>(epi_stage + (warp - 2) * (32 * kI8StagePitch));
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               float o[4];
@@ -412,30 +373,58 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                 const int jj = j + k4;
                 const float tf = fmaf(fmaf((float)(int)v[2][jj], 1.0f / 256.0f, (float)(int)v[1][jj]), 1.0f / 256.0f,
                                       (float)(int)v[0][jj]);
-                int k = ei + ej[jj] - 2 * 1023;
-                k = k < -126 ? -126 : (k > 127 ? 127 : k);
-                const float pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __int_as_float(0x7fc00000) : __int_as_float((k + 127) << 23);
-                if (cosine) {
-                  o[k4] = (float)fast_cosine_distance((double)(tf * pw), ri * my_rn[c * 16 + jj], kind, power);
+                if constexpr (MODE == 0) {
+                  // 2 - 2 g with g = tf * 2^(e_i + e_j): the scaling is exact, so this is the general path's value
+                  asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(prow * __int_as_float(ej[jj]), tf, 2.0f))));
                 } else {
-                  asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
+                  int k = ei + ej[jj] - 2 * 1023;
+                  k = k < -126 ? -126 : (k > 127 ? 127 : k);
+                  const float pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __int_as_float(0x7fc00000) : __int_as_float((k + 127) << 23);
+                  if constexpr (MODE == 2) {
+                    o[k4] = cosine_distance_f32(tf * pw, ri * my_rn[c * 16 + jj], kind, power);
+                  } else {
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(-2.0f, tf * pw, 2.0f))));
+                  }
                 }
               }
-              if (row_ok) {
-                if (vec4 && col0 + j + 4 <= N) {
-                  *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
+              *reinterpret_cast<float4 *>(stg + lane * (kI8StagePitch / 4) + j) = make_float4(o[0], o[1], o[2], o[3]);
+              if (symmetric && row_ok) {  // out[col][row]: the 32 lanes of a warp write 32 consecutive rows
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4)
-                    if (col0 + j + k4 < N) dst[j + k4] = o[k4];
-                }
-                if (symmetric) {  // out[col][row]: the 32 lanes of a warp write 32 consecutive rows
+                for (int k4 = 0; k4 < 4; ++k4)
+                  if (col0 + j + k4 < N) reinterpret_cast<float *>(out)[(size_t)(col0 + j + k4) * ldo + row] = o[k4];
+              }
+            }
+            __syncwarp();
+            if (!(debug_flags & 4)) {
+              const int cq = (lane & 3) * 4;
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4)
-                    if (col0 + j + k4 < N) reinterpret_cast<float *>(out)[(size_t)(col0 + j + k4) * ldo + row] = o[k4];
+              for (int m = 0; m < 4; ++m) {
+                const int r = 8 * m + (lane >> 2);
+                const long long grow = (long long)tm * BM + q * 32 + r;
+                const float4 val = *reinterpret_cast<const float4 *>(stg + r * (kI8StagePitch / 4) + cq);
+                if (grow < M) {
+                  float *dst = reinterpret_cast<float *>(out) + (size_t)grow * ldo + col0 + cq;
+                  if (vec4 && col0 + cq + 4 <= N) {
+                    *reinterpret_cast<float4 *>(dst) = val;
+                  } else {
+                    if (col0 + cq + 0 < N) dst[0] = val.x;
+                    if (col0 + cq + 1 < N) dst[1] = val.y;
+                    if (col0 + cq + 2 < N) dst[2] = val.z;
+                    if (col0 + cq + 3 < N) dst[3] = val.w;
+                  }
                 }
               }
             }
+            __syncwarp();
+          }
+          };
+          if constexpr (COS) {
+            chunk_loop(std::integral_constant<int, 2>{});
+          } else {
+            if (lean)
+              chunk_loop(std::integral_constant<int, 0>{});
+            else
+              chunk_loop(std::integral_constant<int, 1>{});
           }
         } else {
           // fp64 SOAPdistanceNormalized: the six digit sums are folded into two exact 64-bit integers,
