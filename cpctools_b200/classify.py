@@ -26,6 +26,8 @@ __all__ = [
     "getDistancesFromRefNormalized",
     "getDistancesFromInterval",
     "mergeReferences",
+    "saveReferences",
+    "getReferencesFromDataset",
     "applyClassification",
 ]
 
@@ -77,6 +79,25 @@ def mergeReferences(*x: SOAPReferences) -> SOAPReferences:
         if x[0].nmax != i.nmax or x[0].lmax != i.lmax:
             raise ValueError("nmax or lmax are not the same in the two references")
     return SOAPReferences(names, np.concatenate([i.spectra for i in x]), nmax=x[0].nmax, lmax=x[0].lmax)
+
+
+def saveReferences(h5position, targetDatasetName: str, refs: SOAPReferences):
+    """Export a reference dictionary as a gzip-9 dataset with ``nmax`` / ``lmax`` / ``names`` attributes
+    (classify.py:208-229).  ``h5position`` is an ``h5py.File`` / ``h5py.Group`` (anything with
+    ``require_dataset``); host-side storage only, nothing runs on the device."""
+    spectra = np.asarray(refs.spectra)
+    target = h5position.require_dataset(
+        targetDatasetName, shape=spectra.shape, dtype=spectra.dtype, compression="gzip", compression_opts=9
+    )
+    target[:] = spectra
+    for key, value in (("nmax", refs.nmax), ("lmax", refs.lmax), ("names", refs.names)):
+        target.attrs.create(key, value)
+
+
+def getReferencesFromDataset(dataset) -> SOAPReferences:
+    """Rebuild the :class:`SOAPReferences` stored by :func:`saveReferences` (classify.py:232-247)."""
+    attrs = dataset.attrs
+    return SOAPReferences(names=attrs["names"].tolist(), spectra=dataset[:], lmax=attrs["lmax"], nmax=attrs["nmax"])
 
 
 def pairs_device(data, spectra, kind: int, power: int = 1, path: int = _lib.PAIRS_AUTO, out=None, want_argmin=False):

@@ -152,3 +152,36 @@ def test_product_never_imports_the_oracle():
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
             assert "/root/reference" not in src, fn
+
+
+def test_references_round_trip_through_an_hdf5_like_group():
+    """saveReferences / getReferencesFromDataset only use the h5py duck type (classify.py:208-247)."""
+    import cpctools_b200 as S
+
+    class _Attrs(dict):
+        def create(self, key, value):
+            self[key] = np.asarray(value)
+
+    class _Dataset:
+        def __init__(self, shape, dtype, **kw):
+            self.data, self.attrs, self.kw = np.zeros(shape, dtype=dtype), _Attrs(), kw
+
+        def __setitem__(self, key, value):
+            self.data[key] = value
+
+        def __getitem__(self, key):
+            return np.array(self.data[key])
+
+    class _Group(dict):
+        def require_dataset(self, name, shape, dtype, **kw):
+            self[name] = _Dataset(shape, dtype, **kw)
+            return self[name]
+
+    rng = np.random.default_rng(0)
+    refs = S.SOAPReferences(["bulk", "surface", "vertex"], rng.random((3, 576)), 8, 8)
+    grp = _Group()
+    S.saveReferences(grp, "myRefs", refs)
+    assert grp["myRefs"].kw == {"compression": "gzip", "compression_opts": 9}
+    back = S.getReferencesFromDataset(grp["myRefs"])
+    assert back.names == refs.names and back.lmax == 8 and back.nmax == 8 and len(back) == 3
+    np.testing.assert_array_equal(back.spectra, refs.spectra)
