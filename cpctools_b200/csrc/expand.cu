@@ -11,6 +11,8 @@
 // The int32 gather table lives in shared memory and is hoisted into registers per column chunk.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace soapb {
@@ -334,7 +336,8 @@ static int launch_expand(const void *in, void *out, const int32_t *idx, int64_t 
   if (nvec == 0) return SOAP_OK;
   const size_t row_bytes = (size_t)in_stride * sizeof(T);
   // tile of ~40 KB per stage so that two CTAs (4 stages) fit in one SM's shared memory
-  int tv = (int)(40960 / row_bytes);
+  const char *tile_env = getenv("SOAP_EX_TILE");  // experiment: bytes per stage
+  int tv = (int)((tile_env ? atoi(tile_env) : 40960) / row_bytes);
   if (tv < 1) tv = 1;
   if (tv > 64) tv = 64;
   if ((int64_t)tv > nvec) tv = (int)nvec;
@@ -348,10 +351,12 @@ static int launch_expand(const void *in, void *out, const int32_t *idx, int64_t 
   const int vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                      (((size_t)d_full * sizeof(T)) % 16 == 0);
   const int64_t ntiles = (nvec + tv - 1) / tv;
-  const int per_sm = smem * 2 <= (size_t)max_smem_optin() ? 2 : 1;
-  int grid = (int)(ntiles < (int64_t)num_sms() * per_sm ? ntiles : (int64_t)num_sms() * per_sm);
   auto kern = idx ? expand_kernel<T, NORM, true> : expand_kernel<T, NORM, false>;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;  // persistent grid: every CTA that is resident at once, no more
+  SOAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kExpandThreads, smem));
+  per_sm = per_sm < 1 ? 1 : per_sm;
+  int grid = (int)(ntiles < (int64_t)num_sms() * per_sm ? ntiles : (int64_t)num_sms() * per_sm);
   ProfScope prof(SOAP_PROF_EXPAND, stream);
   kern<<<grid, kExpandThreads, smem, stream>>>(static_cast<const T *>(in), static_cast<T *>(out), idx,
                                                 (long long)nvec, in_stride, d_full, tv, bulk_ok, vec_ok);
