@@ -335,9 +335,11 @@ static int launch_expand(const void *in, void *out, const int32_t *idx, int64_t 
                          int in_stride, int d_full, cudaStream_t stream) {
   if (nvec == 0) return SOAP_OK;
   const size_t row_bytes = (size_t)in_stride * sizeof(T);
-  // tile of ~40 KB per stage so that two CTAs (4 stages) fit in one SM's shared memory
   const char *tile_env = getenv("SOAP_EX_TILE");  // experiment: bytes per stage
-  int tv = (int)((tile_env ? atoi(tile_env) : 40960) / row_bytes);
+  // ~40 KB per stage (two to four CTAs per SM); the fp32 expand+normalise kernel also carries the table and
+  // the slot weights and runs best with three CTAs of 32 KB stages (A/B: 0.84 -> 0.89 of the HBM peak)
+  const int tile_bytes = tile_env ? atoi(tile_env) : ((NORM && idx && sizeof(T) == 4) ? 32768 : 40960);
+  int tv = (int)(tile_bytes / row_bytes);
   if (tv < 1) tv = 1;
   if (tv > 64) tv = 64;
   if ((int64_t)tv > nvec) tv = (int)nvec;
