@@ -80,9 +80,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
+// Wait with a watchdog: a hand-shake that cannot complete (a protocol bug, a faulted bulk copy) traps
+// after ~20 s instead of hanging the GPU.  The common case returns from the first poll.
+static __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    for (int i = 0; i < 4096; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
