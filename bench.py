@@ -383,6 +383,17 @@ def run_gpu_arm(args):
         single[f"window_{w}"] = {"kernel_ms": ms, "GBps": nb / ms / 1e6, "frac": nb / ms / 1e6 / peak,
                                  "pairs_per_s": (frames - w) * atoms / ms * 1e3}
     roofline["single_window_calls"] = single
+
+    # the same sweep launch timed ALONE after the GPU has idled: inside the timed region above the SMs run
+    # under sw_power_cap and this kernel (shared-memory bound) follows the SM clock
+    time.sleep(3.0)
+    _lib.profile_enable(True)
+    timelag_device(X, WINDOWS, _lib.KIND_SIMPLE, 1, mult=mult)
+    torch.cuda.synchronize()
+    alone_ms = float(_lib.profile_read(_lib.PROF_TIMELAG)[0])
+    _lib.profile_enable(False)
+    roofline["timed_alone"] = {"kernel_ms": alone_ms, "GBps": algo_bytes / alone_ms / 1e6, "frac": algo_bytes / alone_ms / 1e6 / peak,
+                               "note": "one launch after 3 s of idle (burst clocks); `frac` above is the sustained figure"}
     del X, out
     torch.cuda.empty_cache()
 
