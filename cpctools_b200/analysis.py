@@ -157,8 +157,8 @@ def _pinned_host_tensor(x) -> bool:
 def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom):
     """Pinned host trajectory -> host results with the link kept busy: atom tiles ``x[:, lo:hi, :]`` are
     uploaded on a copy stream (strided ``cudaMemcpy2DAsync`` into one of two device buffers) while the
-    previous tile is processed, and every tile's results are downloaded while the next uploads.
-    The step then costs the H2D time of ``x`` plus the tail of the last tile."""
+    previous tile is processed.  The step then costs the H2D time of ``x`` plus the tail of the last tile and
+    one staged download of the (small) results."""
     th = _device.require_cuda()
     lib = _lib.load()
     F, A, D = (int(v) for v in x.shape)
@@ -174,9 +174,15 @@ def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom):
     main = th.cuda.current_stream()
     copied = [th.cuda.Event() for _ in ranges]
     done = [th.cuda.Event() for _ in ranges]
-    t_host = [th.empty((F - w, A), dtype=th.float64) for w in windows]
-    dt_host = [th.empty((A, F - w - 1), dtype=th.float64) for w in windows] if returnDiff else None
-    pending = []  # device results per tile, kept alive until downloaded
+    # results are assembled on the device in ONE flat buffer (tiny next to the input) and come back through the
+    # pinned staging buffers with a threaded copy: per-tile copies into fresh pageable tensors take their page
+    # faults on one thread and made the step time vary by 10 %
+    sizes = [(F - w) * A for w in windows] + ([A * (F - w - 1) for w in windows] if returnDiff else [])
+    res = th.empty(int(sum(sizes)), dtype=th.float64, device="cuda")
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    nw = len(windows)
+    t_dev = [res[int(offs[k]) : int(offs[k + 1])].view(F - w, A) for k, w in enumerate(windows)]
+    dt_dev = [res[int(offs[nw + k]) : int(offs[nw + k + 1])].view(A, F - w - 1) for k, w in enumerate(windows)] if returnDiff else None
 
     def upload(i):
         lo, hi = ranges[i]
@@ -190,16 +196,6 @@ def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom):
             _lib.check(rc, "soap_copy_rows")
             copied[i].record(copy_stream)
 
-    def download(i):
-        lo, hi = ranges[i]
-        done[i].synchronize()
-        ts, dts = pending[i]
-        for k in range(len(windows)):
-            t_host[k][:, lo:hi] = ts[k]
-            if returnDiff:
-                dt_host[k][lo:hi] = dts[k]
-        pending[i] = None
-
     upload(0)
     for i, (lo, hi) in enumerate(ranges):
         if i + 1 < len(ranges):
@@ -207,13 +203,15 @@ def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom):
         main.wait_event(copied[i])
         X = bufs[i & 1][:, : hi - lo, :] if hi - lo == tile else bufs[i & 1].view(-1)[: F * (hi - lo) * D].view(F, hi - lo, D)
         ts = timelag_device(X, windows, kind, power, mult=mult)
-        dts = [diff_transposed_device(t) for t in ts] if returnDiff else None
+        for k in range(nw):
+            t_dev[k][:, lo:hi] = ts[k]
+            if returnDiff:
+                dt_dev[k][lo:hi] = diff_transposed_device(ts[k])
         done[i].record(main)
-        pending.append((ts, dts))
-        if i >= 1:
-            download(i - 1)  # overlaps the upload of tile i + 1
-    download(len(ranges) - 1)
+    host = th.from_numpy(_device.to_host(res))
+    t_host = [host[int(offs[k]) : int(offs[k + 1])].view(F - w, A) for k, w in enumerate(windows)]
     if returnDiff:
+        dt_host = [host[int(offs[nw + k]) : int(offs[nw + k + 1])].view(A, F - w - 1) for k, w in enumerate(windows)]
         return list(zip(t_host, dt_host))
     return t_host
 
