@@ -194,29 +194,42 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def parse_topo_cpu_affinity(text: str, local: int):
+    """CPU ids next to ``GPU<local>`` in the output of ``nvidia-smi topo -m`` (the "CPU Affinity" column), or
+    None when the table has no such row / column."""
+    header = None
+    for line in text.splitlines():
+        cells = [c.strip() for c in line.replace("\x1b[4m", "").replace("\x1b[0m", "").split("\t") if c.strip()]
+        if not cells:
+            continue
+        if "CPU Affinity" in cells and header is None:
+            header = cells
+            continue
+        if header is not None and cells[0] == f"GPU{local}":
+            col = header.index("CPU Affinity") + 1  # the header has no cell above the row labels
+            if col >= len(cells):
+                return None
+            cpus = set()
+            for part in cells[col].split(","):
+                lo, _, hi = part.partition("-")
+                if not lo.strip().isdigit():
+                    return None
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            return sorted(cpus)
+    return None
+
+
 def bind_to_gpu_numa_node(local: int):
     """Pin this rank's host threads (and so its first-touch / pinned allocations) to the cores next to its
     GPU, as listed by ``nvidia-smi topo -m``: with 8 ranks uploading at once, host buffers on the wrong
     socket halve the end-to-end rate.  Best effort: any failure leaves the affinity untouched."""
     try:
         out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
-        header = None
-        for line in out.splitlines():
-            cells = [c.strip() for c in line.split("\t") if c.strip()]
-            if not cells:
-                continue
-            if "CPU Affinity" in line and header is None:
-                header = cells
-                continue
-            if header is not None and cells[0] == f"GPU{local}":
-                col = header.index("CPU Affinity") + 1  # the header has no cell above the row labels
-                cpus = set()
-                for part in cells[col].split(","):
-                    lo, _, hi = part.partition("-")
-                    cpus.update(range(int(lo), int(hi or lo) + 1))
-                cpus &= os.sched_getaffinity(0)
-                if cpus:
-                    os.sched_setaffinity(0, cpus)
+        cpus = parse_topo_cpu_affinity(out, local)
+        if cpus:
+            cpus = set(cpus) & os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
                 return sorted(cpus)
     except Exception:
         pass

@@ -185,3 +185,23 @@ def test_references_round_trip_through_an_hdf5_like_group():
     back = S.getReferencesFromDataset(grp["myRefs"])
     assert back.names == refs.names and back.lmax == 8 and back.nmax == 8 and len(back) == 3
     np.testing.assert_array_equal(back.spectra, refs.spectra)
+
+
+def test_bench_parses_the_gpu_cpu_affinity_table():
+    """bench.py binds every rank to the cores next to its GPU: the parser of `nvidia-smi topo -m`."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    one = "\t\x1b[4mGPU0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\x1b[0m\nGPU0\t X \t0-15\t0\t\tN/A\n\nLegend:\n"
+    assert bench.parse_topo_cpu_affinity(one, 0) == list(range(16))
+    assert bench.parse_topo_cpu_affinity(one, 1) is None
+    two = ("\tGPU0\tGPU1\tNIC0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\n"
+           "GPU0\t X \tNV18\tPIX\t0-3,64-67\t0\t\tN/A\n"
+           "GPU1\tNV18\t X \tSYS\t32-35\t1\t\tN/A\n"
+           "NIC0\tPIX\tSYS\t X \n")
+    assert bench.parse_topo_cpu_affinity(two, 0) == [0, 1, 2, 3, 64, 65, 66, 67]
+    assert bench.parse_topo_cpu_affinity(two, 1) == [32, 33, 34, 35]
+    assert bench.parse_topo_cpu_affinity("no table here", 0) is None
