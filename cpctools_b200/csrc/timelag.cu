@@ -44,6 +44,10 @@ static size_t tl_smem_bytes(int R, int stride, int upp, int Q, int cw, int mbuf)
 // upper bound on the persistent grid (CTAs resident at once); sizes the per-CTA accumulators in scratch
 static long long tl_max_grid() { return (long long)num_sms() * 4; }
 
+// a CTA owns whole atoms (and sums their pieces on chip) when there are enough atoms to keep every SM busy
+// with little imbalance; with fewer atoms the (atom, piece) items are dealt round robin
+static bool tl_atom_major(int64_t n_atoms) { return n_atoms >= 4ll * num_sms(); }
+
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
@@ -222,14 +226,22 @@ __device__ __forceinline__ double ld_acc(const double *p, uint64_t pol) {
   return v;
 }
 
-// item j of a CTA: its atoms are blockIdx.x, + gridDim.x, ...; ALL pieces of an atom are consecutive items
-// of the same CTA, so that the reducer can add the pieces up before anything goes to DRAM
+// item j of a CTA.  atom_major: its atoms are blockIdx.x, + gridDim.x, ... and ALL pieces of an atom are
+// consecutive items of the same CTA, so that the reducer can add the pieces up before anything goes to DRAM.
+// Otherwise (few atoms: fewer atoms than would keep every SM busy) items (atom, piece) are dealt round robin
+// and every piece writes its own partial sums, which the finalize kernel adds.
 template <int UE>
-__device__ __forceinline__ TlItem tl_item(int j, int split, int upp, int D) {
+__device__ __forceinline__ TlItem tl_item(int j, int split, int upp, int D, bool atom_major) {
   TlItem it;
-  const int k = j / split;
-  it.p = j - k * split;
-  it.a = (long long)blockIdx.x + (long long)k * gridDim.x;
+  if (atom_major) {
+    const int k = j / split;
+    it.p = j - k * split;
+    it.a = (long long)blockIdx.x + (long long)k * gridDim.x;
+  } else {
+    const long long i = (long long)blockIdx.x + (long long)j * gridDim.x;
+    it.a = i / split;
+    it.p = (int)(i - it.a * split);
+  }
   it.e0 = it.p * upp * UE;
   it.pe = min(D - it.e0, upp * UE);  // elements of this piece (> 0)
   it.punits = (it.pe + UE - 1) / UE;
@@ -258,8 +270,11 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
   uint64_t *red_full = empty + nslots;                                    // [1]
   uint64_t *red_empty = red_full + 1;                                     // [1]
 
+  const bool atom_major = cta_acc != nullptr;
   const long long my_atoms = (long long)blockIdx.x < A ? (A - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int n_my = (int)my_atoms * split;
+  const long long n_items = A * split;
+  const int n_my = atom_major ? (int)my_atoms * split
+                              : ((long long)blockIdx.x < n_items ? (int)((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0);
   const int nblk = (int)((F + kBlk - 1) / kBlk);
 
   // prologue (all warps): the ring is zeroed when rows are not 16-byte multiples (the tail unit of a
@@ -288,7 +303,7 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
     const int back = nslots - lag_blocks;
     int s = 0, js = 0, jph = 0, g = 0;
     for (int k = 0; k < n_my; ++k) {
-      const TlItem it = tl_item<UE>(k, split, upp, D);
+      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major);
       const T *xa = X + (size_t)it.a * D + it.e0;
       const int mslot = k & (mbuf - 1);
       for (int b = 0; b < nblk; ++b, ++g) {
@@ -334,12 +349,12 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
     int g = 0;
     const uint64_t pol = l2_policy_evict_last();
     for (int k = 0; k < n_my; ++k) {
-      const TlItem it = tl_item<UE>(k, split, upp, D);
+      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major);
       // pieces 0 .. split-2 leave their running sums in this CTA's accumulator (read back by the same lane for
       // the next piece: L2 traffic only), the last piece writes the totals of the atom
-      double *srow = sums + (size_t)it.a * Q * (size_t)F;
+      double *srow = atom_major ? sums + (size_t)it.a * Q * (size_t)F : sums + ((size_t)it.a * split + it.p) * Q * (size_t)F;
       double *acc_row = cta_acc + (size_t)blockIdx.x * Q * (size_t)nblk * kBlk;
-      const bool first_piece = it.p == 0, last_piece = it.p == split - 1;
+      const bool first_piece = !atom_major || it.p == 0, last_piece = !atom_major || it.p == split - 1;
       for (int b = 0; b < nblk; ++b, ++g) {
         const long long fl = (long long)b * kBlk + lane;
         double prev[Q];
@@ -372,7 +387,7 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
     for (int k = 0; k < NW; ++k) wmod[k] = win[k] % R;
     int s = 0, ph = 0, g = 0;
     for (int k = 0; k < n_my; ++k) {
-      const TlItem it = tl_item<UE>(k, split, upp, D);
+      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major);
       const int my_units = it.punits > warp ? (it.punits - warp + CW - 1) / CW : 0;
       const uint32_t m_addr = msm_addr + (uint32_t)(k & (mbuf - 1)) * upp * 16;
       for (int b = 0; b < nblk; ++b, ++g) {
@@ -524,11 +539,13 @@ static int launch_timelag(const void *X, const void *mult, double *scratch, int6
   long long grid = (long long)sms * per_sm;
   const int force_grid = env_int("SOAP_TL_GRID", 0);
   if (force_grid > 0) grid = force_grid;
-  if (grid > A) grid = A;  // a CTA owns whole atoms (all their pieces)
-  SOAP_REQUIRE(grid <= tl_max_grid(), "soap_timelag: grid %lld exceeds the accumulator area", grid);
-  SOAP_REQUIRE(((long long)A + grid - 1) / grid * pl.split * ((F + kBlk - 1) / kBlk) < 2147483647LL,
+  const bool atom_major = tl_atom_major(A);
+  const long long n_items = (long long)A * pl.split;
+  if (grid > (atom_major ? (long long)A : n_items)) grid = atom_major ? (long long)A : n_items;
+  SOAP_REQUIRE(!atom_major || grid <= tl_max_grid(), "soap_timelag: grid %lld exceeds the accumulator area", grid);
+  SOAP_REQUIRE((n_items + grid - 1) / grid * ((F + kBlk - 1) / kBlk) + (long long)pl.split * ((F + kBlk - 1) / kBlk) < 2147483647LL,
                "soap_timelag: too many blocks per CTA (%lld atoms x %d pieces)", (long long)A, pl.split);
-  double *cta_acc = scratch + (size_t)A * pl.Q * (size_t)F;
+  double *cta_acc = atom_major ? scratch + (size_t)A * pl.Q * (size_t)F : nullptr;
   // X viewed as a 2-D tensor [F][A*D] of 8-byte words; box = 32 frames x one piece (stride bytes).  No L2
   // promotion: the neighbouring pieces of a row are fetched by the same CTA one item later, long after the
   // promoted sectors have left L2 (measured: DRAM reads 1.12x -> 1.08x the algorithmic bytes, (1,) 0.965 -> 0.988)
@@ -556,7 +573,7 @@ static int launch_finalize(const double *scratch, double *t, const int64_t *off,
   dim3 grid((unsigned)((F + 31) / 32), (unsigned)((A + 31) / 32));
   SOAP_REQUIRE(grid.y <= 65535, "soap_timelag: more than 2M atoms per call are not supported");
   timelag_finalize_kernel<NW><<<grid, 256, 0, s>>>(scratch, t, off[0], NW > 1 ? off[1] : 0, NW > 2 ? off[2] : 0,
-                                                  NW > 3 ? off[3] : 0, (long long)F, (long long)A, /*pieces already summed*/ 1,
+                                                  NW > 3 ? off[3] : 0, (long long)F, (long long)A, tl_atom_major(A) ? 1 : pl.split,
                                                   win4, kind, power);
   return check_launch("timelag_finalize_kernel");
 }
@@ -580,6 +597,7 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
   if (!make_plan(n_frames, dim, dtype == SOAP_F64 ? 8 : 4, windows_host, n_windows, pl)) return 0;
   // totals sums[a][q][f] + one accumulator [q][frames padded to 32] per resident CTA
   const size_t padded = (size_t)((n_frames + kBlk - 1) / kBlk) * kBlk;
+  if (!tl_atom_major(n_atoms)) return (size_t)n_atoms * pl.split * pl.Q * (size_t)n_frames * sizeof(double);
   return ((size_t)n_atoms * pl.Q * (size_t)n_frames + (size_t)tl_max_grid() * pl.Q * padded) * sizeof(double);
 }
 

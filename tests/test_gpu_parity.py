@@ -279,6 +279,8 @@ def test_timesoap_sweep_from_compressed_vs_oracle(S, F, A, species, dtype, windo
         (40, 700, 36, np.float64, (1, 3)),    # several work items per persistent CTA (700 > SMs)
         (64, 450, 250, np.float32, (1, 5, 10, 50)),
         (97, 160, 1224, np.float64, (1, 5, 10, 50)),  # rows split into pieces, pieces change inside a CTA
+        (60, 640, 1224, np.float64, (1, 5, 10, 50)),  # enough atoms for the atom-major mode: pieces summed on chip
+        (41, 601, 612, np.float32, (2, 40)),
         (35, 5, 7, np.float64, (2, 4)),       # unaligned rows: element-copy path, several items per CTA
         (35, 300, 7, np.float32, (1, 9)),
     ],
