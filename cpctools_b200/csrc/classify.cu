@@ -364,7 +364,7 @@ extern "C" int soap_classify(const void *X, const void *mult, const double *refw
         const int grid = (int)(ntiles < num_sms() ? ntiles : num_sms());
         CUtensorMap tmap;
         int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, nvec, (int64_t)dim * es / 8, stride / 8, tv,
-                                    CU_TENSOR_MAP_SWIZZLE_NONE);
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE);
         if (rc) return rc;
         ProfScope prof(SOAP_PROF_PAIRS, s);
 #define CT_LAUNCH(T, KM, VP)                                                                                          \
