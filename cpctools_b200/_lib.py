@@ -11,7 +11,7 @@ import os
 import shutil
 import subprocess
 import threading
-from ctypes import c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")

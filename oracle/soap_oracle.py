@@ -17,8 +17,7 @@ the reference so that parity tests read like the reference's tests.
 """
 from __future__ import annotations
 
-import math
-from typing import Callable, Iterable, Sequence
+from typing import Callable, Sequence
 
 import numpy as np
 import scipy.spatial.distance as _ssd

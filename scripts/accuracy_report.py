@@ -15,7 +15,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cpctools_b200 as S  # noqa: E402
 from cpctools_b200 import _lib  # noqa: E402
-from cpctools_b200.analysis import timelag_device  # noqa: E402
 from cpctools_b200.classify import pairs_device  # noqa: E402
 from oracle import soap_oracle as O  # noqa: E402
 from oracle.fake_dataset import dscribe_attrs, synthetic_soap  # noqa: E402

@@ -129,7 +129,6 @@ def main():
 
     # ---- classification against a small dictionary (f1): fused kernel straight from compressed rows
     if want("classify"):
-        import ctypes
         F, A, K = (50, 20000, 8) if args.quick else (200, 50000, 8)
         for Dc, Df, kw in ((324, 576, {}),):
             raw = fill((F * A, Dc), torch.float64)
