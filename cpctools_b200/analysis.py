@@ -112,23 +112,30 @@ def _atom_tiles(x, bytes_per_atom: int):
     return [(lo, min(n_atoms, lo + per_tile)) for lo in range(0, n_atoms, per_tile)]
 
 
-def _tiled(x, windows, kind, power, mult, returnDiff):
+def _run_windows(X, windows, kind, power, mult, simple):
+    """One device tile: the time-lag kernel, or (``simple``) the row stitching of ``timeSOAPsimple``."""
+    if simple:
+        return [_simple_rows(X, windows[0])]
+    return timelag_device(X, windows, kind, power, mult=mult)
+
+
+def _tiled(x, windows, kind, power, mult, returnDiff, simple: bool = False):
     """Run the time-lag kernel over atom tiles of ``x``; returns per window ``t`` (and ``dt``) in the
-    container type of ``x``."""
+    container type of ``x``.  ``simple``: ``windows == [w]`` and the rows are those of ``timeSOAPsimple``."""
     th = _device.require_cuda()
     F, D = int(x.shape[0]), int(x.shape[2])
     itemsize = 4 if str(getattr(x, "dtype", "")).endswith("float32") else 8
     per_atom = F * D * itemsize + F * 8 * (len(windows) + 1) * 8
     if _pinned_host_tensor(x) and F * int(x.shape[1]) * D * itemsize >= PIPELINE_MIN_BYTES:
-        return _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom)
+        return _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom, simple)
     tiles = _atom_tiles(x, per_atom)
     if len(tiles) == 1:
         X = _device.as_float_tensor(x)
-        return [_finish(t, x, returnDiff) for t in timelag_device(X, windows, kind, power, mult=mult)]
+        return [_finish(t, x, returnDiff) for t in _run_windows(X, windows, kind, power, mult, simple)]
     outs = [[] for _ in windows]
     for lo, hi in tiles:
         X = _device.as_float_tensor(x[:, lo:hi, :])
-        for k, t in enumerate(timelag_device(X, windows, kind, power, mult=mult)):
+        for k, t in enumerate(_run_windows(X, windows, kind, power, mult, simple)):
             outs[k].append(_finish(t, x, returnDiff))
         del X
     res = []
@@ -154,7 +161,7 @@ def _pinned_host_tensor(x) -> bool:
             and x.dtype in (_device.torch.float32, _device.torch.float64))
 
 
-def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom):
+def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom, simple: bool = False):
     """Pinned host trajectory -> host results with the link kept busy: atom tiles ``x[:, lo:hi, :]`` are
     uploaded on a copy stream (strided ``cudaMemcpy2DAsync`` into one of two device buffers) while the
     previous tile is processed.  The step then costs the H2D time of ``x`` plus the tail of the last tile and
@@ -202,7 +209,7 @@ def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom):
             upload(i + 1)
         main.wait_event(copied[i])
         X = bufs[i & 1][:, : hi - lo, :] if hi - lo == tile else bufs[i & 1].view(-1)[: F * (hi - lo) * D].view(F, hi - lo, D)
-        ts = timelag_device(X, windows, kind, power, mult=mult)
+        ts = _run_windows(X, windows, kind, power, mult, simple)
         for k in range(nw):
             t_dev[k][:, lo:hi] = ts[k]
             if returnDiff:
@@ -323,8 +330,11 @@ def timeSOAPsimple(SOAPTrajectory, window: int = 1, stride: int = None, backward
     :func:`_simple_rows`); use :func:`timeSOAP` for true lag-``window`` distances.
     """
     _validate(int(SOAPTrajectory.shape[0]), window, stride)
-    X = _device.as_float_tensor(SOAPTrajectory)
-    return _finish(_simple_rows(X, int(window)), SOAPTrajectory, returnDiff)
+    if len(SOAPTrajectory.shape) != 3:
+        raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
+    # atoms are independent for the Euclidean kind too: host trajectories larger than HBM go through the same
+    # atom tiles (and the pinned upload pipeline) as timeSOAP, the rows are stitched per tile
+    return _tiled(SOAPTrajectory, [int(window)], _lib.KIND_EUCLID, 1, None, returnDiff, simple=True)[0]
 
 
 def getTimeSOAPSimple(soapDataset, window: int = 1, stride: int = None, backward: bool = False):

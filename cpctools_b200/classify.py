@@ -159,7 +159,7 @@ def _prepared_blocks(SOAPTrajData, references: SOAPReferences, doNormalize: bool
     th = _device.require_cuda()
     lib = _lib.load()
     F, A = int(SOAPTrajData.shape[0]), int(SOAPTrajData.shape[1])
-    first, last, _ = (frames or slice(None)).indices(F)
+    first, last = _frame_interval(frames, F)
     Dref = int(np.asarray(references.spectra).shape[-1])
     Dc = int(SOAPTrajData.shape[-1])
     convert = Dc != Dref
@@ -186,6 +186,14 @@ def _prepared_blocks(SOAPTrajData, references: SOAPReferences, doNormalize: bool
             _lib.check(rc, "expand")
             rows = out
         yield lo, hi, rows
+
+
+def _frame_interval(frames, n_frames: int):
+    """(first, last) of a contiguous frame slice; a strided slice would silently change the result's shape."""
+    first, last, step = (frames or slice(None)).indices(n_frames)
+    if step != 1:
+        raise ValueError("the frame interval must be contiguous (step 1)")
+    return first, last
 
 
 #: dictionaries up to this many references take the fused kernel (expansion folded into the references)
@@ -224,7 +232,7 @@ def _fused_blocks(SOAPTrajData, setup, kind, power, doNormalize, want_dist, fram
     th = _device.require_cuda()
     lib = _lib.load()
     F, A = int(SOAPTrajData.shape[0]), int(SOAPTrajData.shape[1])
-    first, last, _ = (frames or slice(None)).indices(F)
+    first, last = _frame_interval(frames, F)
     Dc, K = setup["Dc"], setup["K"]
     up = _Uploader(th)
     budget_frames = max(1, (4 << 30) // max(1, A * Dc * 8))
@@ -259,7 +267,7 @@ def getDistancesFromInterval(SOAPTrajData, references: SOAPReferences, distanceC
     kind, power = resolve_distance(distanceCalculator)
     th = _device.require_cuda()
     F, A = int(SOAPTrajData.shape[0]), int(SOAPTrajData.shape[1])
-    first, last, _ = (interval or slice(None)).indices(F)
+    first, last = _frame_interval(interval, F)
     K = len(references)
     result = np.zeros((max(last - first, 0), A, K))
     setup = _fused_setup(SOAPTrajData, references, kind)

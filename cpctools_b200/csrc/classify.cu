@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(kClsThreads, 2)
         } else {
           d = soap_epilogue(uv, uu, ref_norm2[j], kind, power);  // scale invariant in x
         }
+        // the reference stores each frame's distances as data.dtype (classify.py:113) before amin / argmin
+        if constexpr (sizeof(T) == 4) d = (double)(float)d;
         if (dist_out && lane == 0) dist_out[(size_t)v * K + j] = d;
         if (best_j < 0 || cls_better(d, j, best_v, best_j)) { best_v = d; best_j = j; }
       }
@@ -196,6 +198,8 @@ __global__ void __launch_bounds__(kCtThreads, 1)
             for (int w = 0; w < kCtWarps; ++w) uv += r[((size_t)w * (K + 1) + k + 1) * TV + vl];
             d[k] = (kind == SOAP_KIND_NORMALIZED) ? sqrt(fabs(2.0 - 2.0 * (uv / nu)))
                                                   : soap_epilogue(uv, uu, ref_norm2[k], kind, power);
+            // the reference stores each frame's distances as data.dtype (classify.py:113) before amin / argmin
+            if constexpr (sizeof(T) == 4) d[k] = (double)(float)d[k];
           }
         }
 #pragma unroll

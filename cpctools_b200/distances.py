@@ -82,21 +82,66 @@ _KINDS = {
 }
 
 
-def resolve_distance(fn) -> "tuple[int, int]":
-    """(kind, power) for one of the built-in distances, ``functools.partial(SOAPdistance, n=k)`` included."""
-    if isinstance(fn, functools.partial):
-        base = fn.func
-        if base in (SOAPdistance, kernelSOAPdistance, kernelSoap) and not fn.args:
-            extra = set(fn.keywords) - {"n"}
-            if not extra:
-                n = int(fn.keywords.get("n", 1))
-                return (_lib.KIND_DOT if base is kernelSoap else _lib.KIND_KERNEL), n
-        raise NotImplementedError(f"unsupported partial distance {fn!r}")
+_BY_NAME = {
+    "simpleSOAPdistance": (_lib.KIND_SIMPLE, 1),
+    "SOAPdistance": (_lib.KIND_KERNEL, 1),
+    "kernelSOAPdistance": (_lib.KIND_KERNEL, 1),
+    "SOAPdistanceNormalized": (_lib.KIND_NORMALIZED, 1),
+    "simpleKernelSoap": (_lib.KIND_COSCLIP, 1),
+    "kernelSoap": (_lib.KIND_DOT, None),  # the power is a required argument (distances.py:38)
+}
+
+
+def _known(fn):
+    """(kind, power) of a built-in distance: this module's functions by identity, the reference package's own
+    ``SOAPify.distances.*`` (what existing user scripts import) by name + module."""
     try:
-        return _KINDS[fn]
-    except (KeyError, TypeError):
+        if fn in _KINDS:
+            return _KINDS[fn]
+    except TypeError:
+        return None
+    if fn is kernelSoap:
+        return _BY_NAME["kernelSoap"]
+    mod = getattr(fn, "__module__", "") or ""
+    if mod.endswith("SOAPify.distances") or mod.endswith("cpctools_b200.distances"):
+        return _BY_NAME.get(getattr(fn, "__name__", ""))
+    return None
+
+
+def resolve_distance(fn) -> "tuple[int, int]":
+    """(kind, power) for one of the built-in distances.  Accepted: the functions of this module and of the
+    reference's ``SOAPify.distances`` (matched by module + name), wrappers made with ``functools.wraps``
+    (followed through ``__wrapped__``) and ``functools.partial`` chains that only bind the power ``n``
+    (``kernelSoap`` needs it, as in the reference).  Anything else raises ``NotImplementedError``."""
+    power = None
+    seen = 0
+    base = fn
+    while seen < 16:
+        seen += 1
+        if isinstance(base, functools.partial):
+            if base.args or set(base.keywords) - {"n"}:
+                raise NotImplementedError(f"unsupported partial distance {fn!r}: only the power n may be bound")
+            if power is None and "n" in base.keywords:  # the outermost binding wins, like a call would
+                power = int(base.keywords["n"])
+            base = base.func
+            continue
+        if _known(base) is None and hasattr(base, "__wrapped__"):
+            base = base.__wrapped__
+            continue
+        break
+    found = _known(base)
+    if found is None:
         raise NotImplementedError(
             "cpctools_b200 runs the built-in SOAP distances on the GPU (simpleSOAPdistance, SOAPdistance, "
-            "functools.partial(SOAPdistance, n=k), SOAPdistanceNormalized); an arbitrary Python callable "
-            f"would need a CPU loop, which this package does not have: {fn!r}"
-        ) from None
+            "functools.partial(SOAPdistance, n=k), SOAPdistanceNormalized, also when imported from SOAPify.distances "
+            "or wrapped with functools.wraps); an arbitrary Python callable would need a CPU loop, which this "
+            f"package does not have: {fn!r}"
+        )
+    kind, dflt = found
+    if power is not None and kind not in (_lib.KIND_KERNEL, _lib.KIND_DOT):
+        raise NotImplementedError(f"unsupported partial distance {fn!r}: this distance takes no power")
+    if power is None:
+        if dflt is None:
+            raise TypeError("kernelSoap() missing 1 required positional argument: 'n'")
+        power = dflt
+    return kind, power

@@ -43,6 +43,18 @@ def transitionMatrixFromSOAPClassification(data, stride: int = 1, window: "int|N
     if states.dtype != th.int32:
         states = states.to(th.int32)
     counts = th.empty((n_classes, n_classes), dtype=th.int64, device=states.device)
+    to_frames = th.arange(int(window), n_frames, int(stride), device=states.device)
+    if n_atoms and to_frames.numel():
+        # transMat[classFrom, classTo] is numpy indexing in the reference (transitions/__init__.py:44-47): a
+        # negative state counts from the end (-1 = the last class, the "error" class of its docstring) and a
+        # state outside [-n_classes, n_classes) raises IndexError.  Only the frames the loop visits matter.
+        visited = states[th.unique(th.cat((to_frames, to_frames - int(window))))]
+        lo, hi = int(visited.min()), int(visited.max())
+        if lo < -n_classes or hi >= n_classes:
+            bad = hi if hi >= n_classes else lo
+            raise IndexError(f"index {bad} is out of bounds for axis 0 with size {n_classes}")
+        if lo < 0:
+            states = th.where(states < 0, states + n_classes, states).contiguous()
     if n_classes and n_atoms and n_frames:
         rc = _lib.load().soap_transition_counts(
             states.data_ptr(), n_frames, n_atoms, n_classes, int(window), int(stride), counts.data_ptr(), _device.stream_ptr()

@@ -231,6 +231,14 @@ def gen_transitions(S):
             rts = S.calculateResidenceTimesFromClassification(cls, window=window, stride=stride)
             for state, times in enumerate(rts):
                 out[f"rt_{name}w{window}_s{stride}_{state}"] = np.asarray(times)
+    # a classification with unclassified (-1) entries and an "error" legend entry, as the docstring of
+    # calculateTransitionMatrix suggests: numpy indexing makes -1 the LAST class (transitions/__init__.py:44-47)
+    err = np.random.default_rng(777).integers(-1, 5, size=(40, 23))
+    out["refs_err"] = err
+    ecls = S.SOAPclassification(np.zeros(err.shape), err, ["a", "b", "c", "d", "e", "error"])
+    for stride, window in ((1, None), (2, 7)):
+        out[f"tm_err_s{stride}_w{window}"] = S.transitionMatrixFromSOAPClassification(ecls, stride, window)
+        out[f"tmn_err_s{stride}_w{window}"] = S.transitionMatrixFromSOAPClassificationNormalized(ecls, stride, window)
     return out
 
 

@@ -5,21 +5,24 @@ evaluations that merely sum in a different order differ by ``~eps / d**2`` relat
 The reference itself returns 2e-8 instead of 0 (``SOAPdistanceNormalized(x, x)``) or NaN
 (``SOAPdistance(x, x)`` when rounding gives k > 1).  The rule therefore is
 
-* ``d**2`` (equivalently the kernel value ``k``) agrees to ``atol`` ABSOLUTE:
-  1e-12 for the fp64 path, 1e-6 for the fp32 / 3xTF32 path (BASELINE.json north_star);
-* ``d`` agrees to the same number RELATIVE wherever ``d >= d_rel_min``: 0.1 for fp64 and 0.5
-  for the fp32 path (rel err of d = err(k) / d^2; an fp32 dot of O(1000) terms carries
-  err(k) ~ 2e-8 even with double accumulation of the 8-term fp32 chains, i.e. 2e-6 at d = 0.1
-  -- the reference's own float32 numpy path is less accurate than that);
+* ``d**2`` (equivalently the kernel value ``k``) agrees to ``atol`` ABSOLUTE: 1e-12 for the fp64 path;
+  for float32 DATA what the kernels achieve against the fp64 oracle on the same (float32-rounded) inputs,
+  not merely the 1e-6 of BASELINE.json's north_star: 2e-7 for the time-lag kernels (measured 4.2e-8,
+  ``profiles/r01_accuracy.txt``), 5e-7 for the pair kernels (int8 x 3 digits: measured 2.2e-7); 1e-6 only
+  where the expected values are the REFERENCE's own float32 arithmetic (``f32_ref``: numpy's float32 dot is
+  itself 1.4e-6 away from the exact value);
+* ``d`` agrees RELATIVE to 1e-12 (fp64) / 1e-6 (float32 data) wherever ``d >= d_rel_min``: 0.1 for fp64,
+  0.25 for the float32 time-lag path and 0.5 for the float32 pair path (rel err of d = err(k) / (2 d^2));
 * NaNs: a NaN on either side is accepted only against NaN or against ``d**2 <= atol`` on the
   other side (both are "k rounded to just above / just below 1").
 """
 import numpy as np
 
-TOL = {"f64": 1e-12, "f32": 1e-6}
-
-
-D_REL_MIN = {"f64": 0.1, "f32": 0.5}
+#: absolute tolerance on d**2 per path
+TOL2 = {"f64": 1e-12, "f32": 5e-7, "f32_timelag": 2e-7, "f32_ref": 1e-6}
+#: relative tolerance on d (where d >= D_REL_MIN)
+TOL = {"f64": 1e-12, "f32": 1e-6, "f32_timelag": 1e-6, "f32_ref": 1e-6}
+D_REL_MIN = {"f64": 0.1, "f32": 0.5, "f32_timelag": 0.25, "f32_ref": 0.5}
 
 
 def assert_distance_parity(got, want, path="f64", d_rel_min=None, what=""):
@@ -27,14 +30,14 @@ def assert_distance_parity(got, want, path="f64", d_rel_min=None, what=""):
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
-    tol = TOL[path]
+    tol, tol2 = TOL[path], TOL2[path]
     gn, wn = np.isnan(got), np.isnan(want)
     only_g, only_w = gn & ~wn, wn & ~gn
-    assert (want[only_g] ** 2 <= tol).all(), f"{what}: NaN where the oracle has a finite distance"
-    assert (got[only_w] ** 2 <= tol).all(), f"{what}: finite distance where the oracle has NaN"
+    assert (want[only_g] ** 2 <= tol2).all(), f"{what}: NaN where the oracle has a finite distance"
+    assert (got[only_w] ** 2 <= tol2).all(), f"{what}: finite distance where the oracle has NaN"
     ok = ~(gn | wn)
     err2 = np.abs(got[ok] ** 2 - want[ok] ** 2)
-    assert err2.size == 0 or err2.max() <= tol, f"{what}: max |d^2 - d^2_ref| = {err2.max():.3e} > {tol}"
+    assert err2.size == 0 or err2.max() <= tol2, f"{what}: max |d^2 - d^2_ref| = {err2.max():.3e} > {tol2}"
     big = ok & (want >= d_rel_min)
     if big.any():
         rel = np.abs(got[big] - want[big]) / want[big]

@@ -112,6 +112,25 @@ def test_distance_dispatch():
     assert resolve_distance(S.SOAPdistanceNormalized) == (_lib.KIND_NORMALIZED, 1)
     with pytest.raises(NotImplementedError):
         resolve_distance(np.dot)
+    # wrappers (functools.wraps), partial chains, kernelSoap needs its power like the reference
+    @functools.wraps(S.SOAPdistanceNormalized)
+    def logged(x, y):
+        return S.SOAPdistanceNormalized(x, y)
+
+    assert resolve_distance(logged) == (_lib.KIND_NORMALIZED, 1)
+    assert resolve_distance(functools.partial(functools.partial(S.SOAPdistance, n=2), n=5)) == (_lib.KIND_KERNEL, 5)
+    assert resolve_distance(functools.partial(S.kernelSoap, n=4)) == (_lib.KIND_DOT, 4)
+    with pytest.raises(TypeError):
+        resolve_distance(functools.partial(S.kernelSoap))
+    with pytest.raises(NotImplementedError):
+        resolve_distance(functools.partial(S.SOAPdistance, 1.0))
+    with pytest.raises(NotImplementedError):
+        resolve_distance(functools.partial(S.simpleSOAPdistance, n=2))
+    with pytest.raises(NotImplementedError):
+        resolve_distance(lambda x, y: 0.0)
+    # the reference package's own functions (what an existing script imports) are matched by module + name
+    ref = type("f", (), {"__module__": "SOAPify.distances", "__name__": "simpleSOAPdistance", "__call__": lambda s, x, y: 0})()
+    assert resolve_distance(ref) == (_lib.KIND_SIMPLE, 1)
     assert S.tempoSOAP.__doc__ and S.getDistancesFromInterval and S.fillSOAPVectorFromQuip
 
 
