@@ -66,6 +66,7 @@ def _needs_rebuild() -> bool:
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [
         os.path.join(CSRC, "common.cuh"),
         os.path.join(CSRC, "tc05.cuh"),
+        os.path.join(CSRC, "timelag_rb.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "soap_b200.h"),
     ]
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))

@@ -512,6 +512,96 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+}  // namespace soapb
+#include "timelag_rb.cuh"
+namespace soapb {
+
+// The register-blocked kernel is OPT-IN (SOAP_TL_RB=1): on B200 it is slower than timelag_kernel (0.43 against
+// 0.79 of the HBM peak for the 4-window fp64 sweep, profiles/r02_timelag_rb_ncu.txt).  It does cut the shared-memory
+// wavefronts as designed (pipe 35 % busy), but 7 frames per lane means 112-frame blocks, i.e. only 4 consumer
+// warps = ONE per scheduler, and a single warp issues an instruction every ~4.7 cycles on this SM (fixed-latency
+// "wait" stalls between dependent issues that a second warp would hide).  A second warp per scheduler doubles the
+// per-block hand-over of partial sums (35 values per lane for 3.5 units of work).  Kept, with its parity tests, as
+// the measured record of that design; it applies to TMA-able rows, cosine-type kinds, windows <= 56 frames with
+// at most one of them beyond the 10-frame register history.
+struct RbChoice {
+  bool use;
+  int ns, nl, hist;
+  int w[4];     // windows sorted ascending
+  int perm[4];  // w[k] = windows[perm[k]]
+};
+static RbChoice rb_choose(int64_t F, int64_t A, int D, int es, const int *windows, int nw, int kind, bool bulk_ok) {
+  RbChoice ch;
+  memset(&ch, 0, sizeof(ch));
+  const int mode = env_int("SOAP_TL_RB", -1);
+  if (mode != 1 || !bulk_ok || kind == SOAP_KIND_EUCLID || nw < 1 || nw > 4) return ch;
+  for (int k = 0; k < nw; ++k) ch.perm[k] = k;
+  for (int i = 1; i < nw; ++i)
+    for (int j = i; j > 0 && windows[ch.perm[j]] < windows[ch.perm[j - 1]]; --j) {
+      const int t = ch.perm[j];
+      ch.perm[j] = ch.perm[j - 1];
+      ch.perm[j - 1] = t;
+    }
+  for (int k = 0; k < nw; ++k) {
+    ch.w[k] = windows[ch.perm[k]];
+    if (ch.w[k] <= kRbHist) ++ch.ns, ch.hist = ch.w[k];
+    else if (ch.w[k] <= kRbMaxLag) ++ch.nl;
+    else return ch;
+  }
+  if (ch.nl > 1) return ch;
+  if ((D * es) % 16) return ch;
+  if ((int64_t)A * D * es / 8 >= 2147483647LL) return ch;
+  ch.use = true;
+  return ch;
+}
+
+template <typename T, int NS, int NL>
+static int launch_timelag_rb(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D, const RbPlan &pl,
+                             const RbChoice &ch, cudaStream_t s) {
+  auto kern = timelag_rb_kernel<T, NS, NL>;
+  SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  long long grid = num_sms();
+  const int force_grid = env_int("SOAP_TL_GRID", 0);
+  if (force_grid > 0) grid = force_grid;
+  if (grid > A) grid = A;
+  SOAP_REQUIRE(grid <= tl_max_grid(), "soap_timelag: grid %lld exceeds the accumulator area", grid);
+  const int64_t nblk = (F + kRbB - 1) / kRbB;
+  SOAP_REQUIRE(((A + grid - 1) / grid) * pl.pieces * nblk < 2147483647LL, "soap_timelag: too many blocks per CTA");
+  // scratch: totals sums[a][q][f] | per-CTA accumulators [grid][q][frames padded to blocks] | shifted multiplicities
+  double *cta_acc = scratch + (size_t)A * pl.Q * (size_t)F;
+  const size_t padded = (size_t)nblk * kRbB;
+  T *table = reinterpret_cast<T *>((reinterpret_cast<uintptr_t>(cta_acc + (size_t)tl_max_grid() * pl.Q * padded) + 127) & ~(uintptr_t)127);
+  const int units_total = pl.pieces * pl.c * 8;
+  rb_mult_setup_kernel<T><<<32, 256, 0, s>>>(static_cast<const T *>(mult), table, D, units_total);
+  int rc = check_launch("rb_mult_setup_kernel");
+  if (rc) return rc;
+  // X as [F][A*D] 8-byte words; one map per box width (1..4 lines of 16 words), 56 frames per box, no L2 promotion
+  CUtensorMap tm[4];
+  memset(tm, 0, sizeof(tm));
+  const int64_t row_words = (int64_t)A * D * (int64_t)sizeof(T) / 8;
+  for (int st = 0; st < pl.st.n; ++st) {
+    const int k = pl.st.k[st];
+    rc = make_tensor_map_2d(&tm[k - 1], X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, 16 * k, kRbBox,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+  }
+  const int4 win4 = make_int4(ch.w[0], ch.w[1], ch.w[2], ch.w[3]);
+  ProfScope prof(SOAP_PROF_TIMELAG, s);
+  kern<<<(unsigned)grid, kRbThreads, pl.smem, s>>>(table, scratch, cta_acc, (long long)F, (long long)A, pl.n_units, pl.c,
+                                                   pl.pieces, (int)pl.mult_elems, win4, ch.hist, env_int("SOAP_RB_DIAG", 0), pl.st, tm[0], tm[1], tm[2], tm[3]);
+  return check_launch("timelag_rb_kernel");
+}
+
+template <typename T>
+static int dispatch_timelag_rb(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D, const RbPlan &pl,
+                               const RbChoice &ch, cudaStream_t s) {
+#define RB_CASE(NS, NL) \
+  if (ch.ns == NS && ch.nl == NL) return launch_timelag_rb<T, NS, NL>(X, mult, scratch, F, A, D, pl, ch, s);
+  RB_CASE(1, 0) RB_CASE(2, 0) RB_CASE(3, 0) RB_CASE(4, 0) RB_CASE(0, 1) RB_CASE(1, 1) RB_CASE(2, 1) RB_CASE(3, 1)
+#undef RB_CASE
+  return set_error(SOAP_EINVAL, "soap_timelag: no register-blocked variant for %d + %d windows", ch.ns, ch.nl);
+}
+
 template <typename T, int NW, bool HM>
 static int launch_timelag(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D,
                           const TimelagPlan &pl, const int *w, int kind, int bulk_ok, cudaStream_t s) {
@@ -568,13 +658,12 @@ static int launch_timelag(const void *X, const void *mult, double *scratch, int6
 
 template <int NW>
 static int launch_finalize(const double *scratch, double *t, const int64_t *off, int64_t F, int64_t A,
-                           const TimelagPlan &pl, const int *w, int kind, int power, cudaStream_t s) {
+                           int split, const int *w, int kind, int power, cudaStream_t s) {
   const int4 win4 = make_int4(w[0], NW > 1 ? w[1] : 0, NW > 2 ? w[2] : 0, NW > 3 ? w[3] : 0);
   dim3 grid((unsigned)((F + 31) / 32), (unsigned)((A + 31) / 32));
   SOAP_REQUIRE(grid.y <= 65535, "soap_timelag: more than 2M atoms per call are not supported");
   timelag_finalize_kernel<NW><<<grid, 256, 0, s>>>(scratch, t, off[0], NW > 1 ? off[1] : 0, NW > 2 ? off[2] : 0,
-                                                  NW > 3 ? off[3] : 0, (long long)F, (long long)A, tl_atom_major(A) ? 1 : pl.split,
-                                                  win4, kind, power);
+                                                  NW > 3 ? off[3] : 0, (long long)F, (long long)A, split, win4, kind, power);
   return check_launch("timelag_finalize_kernel");
 }
 
@@ -593,12 +682,25 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
                                              const int *windows_host, int n_windows) {
   if (n_frames <= 0 || n_atoms <= 0 || dim <= 0 || !windows_host || n_windows < 1 || n_windows > SOAP_MAX_WINDOWS)
     return 0;
+  const int es = dtype == SOAP_F64 ? 8 : 4;
+  const int Q = n_windows + 1;
+  // register-blocked kernel (whatever the caller's pointers and kind turn out to be, the area covers it): totals
+  // sums[a][q][f] + one accumulator per resident CTA + the 8 shifted multiplicity tables
+  size_t rb_bytes = 0;
+  RbPlan rp;
+  if (rb_make_plan(dim, es, n_windows, rp)) {
+    const size_t padded = (size_t)((n_frames + kRbB - 1) / kRbB) * kRbB;
+    rb_bytes = ((size_t)n_atoms * Q * (size_t)n_frames + (size_t)tl_max_grid() * Q * padded) * sizeof(double) +
+               8 * rp.mult_elems * es + 256;
+  }
   TimelagPlan pl;
-  if (!make_plan(n_frames, dim, dtype == SOAP_F64 ? 8 : 4, windows_host, n_windows, pl)) return 0;
+  if (!make_plan(n_frames, dim, es, windows_host, n_windows, pl)) return rb_bytes;
   // totals sums[a][q][f] + one accumulator [q][frames padded to 32] per resident CTA
   const size_t padded = (size_t)((n_frames + kBlk - 1) / kBlk) * kBlk;
-  if (!tl_atom_major(n_atoms)) return (size_t)n_atoms * pl.split * pl.Q * (size_t)n_frames * sizeof(double);
-  return ((size_t)n_atoms * pl.Q * (size_t)n_frames + (size_t)tl_max_grid() * pl.Q * padded) * sizeof(double);
+  size_t bytes = tl_atom_major(n_atoms)
+                     ? ((size_t)n_atoms * pl.Q * (size_t)n_frames + (size_t)tl_max_grid() * pl.Q * padded) * sizeof(double)
+                     : (size_t)n_atoms * pl.split * pl.Q * (size_t)n_frames * sizeof(double);
+  return bytes > rb_bytes ? bytes : rb_bytes;
 }
 
 extern "C" int soap_timelag(const void *X, const void *mult, double *t, const int64_t *t_offsets_host,
@@ -611,21 +713,38 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
   int rc = check_windows(n_frames, windows_host, n_windows, "soap_timelag");
   if (rc) return rc;
   const int es = dtype == SOAP_F64 ? 8 : 4;
-  TimelagPlan pl;
-  if (!make_plan(n_frames, dim, es, windows_host, n_windows, pl))
-    return set_error(SOAP_EUNSUPPORTED, "soap_timelag: window %d needs more shared memory than one SM has", pl.max_lag);
   // TMA path: 16-byte aligned base pointers and rows that are whole 16-byte units
   int bulk_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (((size_t)dim * es) % 16 == 0) &&
                 ((reinterpret_cast<uintptr_t>(mult) & 15) == 0);
-  if (bulk_ok) bulk_ok |= env_int("SOAP_TL_DIAG", 0) & 30;
   auto s = static_cast<cudaStream_t>(stream);
   auto sc = static_cast<double *>(scratch);
+  {
+    const RbChoice ch = rb_choose(n_frames, n_atoms, dim, es, windows_host, n_windows, kind, bulk_ok != 0);
+    RbPlan rp;
+    if (ch.use && rb_make_plan(dim, es, n_windows, rp)) {
+      rc = dtype == SOAP_F64 ? dispatch_timelag_rb<double>(X, mult, sc, n_frames, n_atoms, dim, rp, ch, s)
+                             : dispatch_timelag_rb<float>(X, mult, sc, n_frames, n_atoms, dim, rp, ch, s);
+      if (rc) return rc;
+      int64_t off[4] = {0, 0, 0, 0};
+      for (int k = 0; k < n_windows; ++k) off[k] = t_offsets_host[ch.perm[k]];
+      switch (n_windows) {
+        case 1: return launch_finalize<1>(sc, t, off, n_frames, n_atoms, 1, ch.w, kind, power, s);
+        case 2: return launch_finalize<2>(sc, t, off, n_frames, n_atoms, 1, ch.w, kind, power, s);
+        case 3: return launch_finalize<3>(sc, t, off, n_frames, n_atoms, 1, ch.w, kind, power, s);
+        default: return launch_finalize<4>(sc, t, off, n_frames, n_atoms, 1, ch.w, kind, power, s);
+      }
+    }
+  }
+  TimelagPlan pl;
+  if (!make_plan(n_frames, dim, es, windows_host, n_windows, pl))
+    return set_error(SOAP_EUNSUPPORTED, "soap_timelag: window %d needs more shared memory than one SM has", pl.max_lag);
+  if (bulk_ok) bulk_ok |= env_int("SOAP_TL_DIAG", 0) & 30;
 #define TL_CASE(T, NW)                                                                                          \
   case NW:                                                                                                      \
     rc = mult ? launch_timelag<T, NW, true>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, s)  \
               : launch_timelag<T, NW, false>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, s); \
     if (rc) return rc;                                                                                          \
-    return launch_finalize<NW>(sc, t, t_offsets_host, n_frames, n_atoms, pl, windows_host, kind, power, s);
+    return launch_finalize<NW>(sc, t, t_offsets_host, n_frames, n_atoms, tl_atom_major(n_atoms) ? 1 : pl.split, windows_host, kind, power, s);
   if (dtype == SOAP_F64) {
     switch (n_windows) { TL_CASE(double, 1) TL_CASE(double, 2) TL_CASE(double, 3) TL_CASE(double, 4) }
   } else {

@@ -315,6 +315,66 @@ def test_timelag_persistent_stream_edge_shapes(S, F, A, D, dtype, windows, monke
         assert_array_equal(t.cpu().numpy(), t2.cpu().numpy())
 
 
+@pytest.mark.parametrize(
+    "F,A,D,dtype,windows",
+    [
+        (300, 9, 1224, np.float64, (1, 5, 10, 50)),   # the benchmark sweep: 3 register windows + 1 ring window
+        (300, 9, 1224, np.float32, (1, 5, 10, 50)),   # fp32 rows start at 4 different phases of a 128-byte line
+        (113, 7, 1198, np.float64, (1, 10)),          # raw quippy rows (599 units): every phase, one frame past a block
+        (112, 5, 324, np.float64, (50,)),             # exactly one block, ring window only
+        (225, 6, 324, np.float32, (2, 3, 7, 9)),      # four register windows
+        (57, 11, 576, np.float64, (56, 4)),           # the longest window the ring keeps; unsorted windows
+        (130, 4, 6, np.float64, (1, 5, 10, 50)),      # rows shorter than a line (3 units): several atoms per line
+        (40, 13, 20, np.float32, (3, 39)),            # fewer frames than a block
+        (260, 3, 2048, np.float64, (1, 56)),          # rows that start and end on a line (no masked units)
+        (500, 160, 1224, np.float64, (1, 5, 10, 50)), # more atoms than CTAs: several atoms per CTA
+    ],
+)
+def test_timelag_register_blocked_kernel(S, F, A, D, dtype, windows, monkeypatch):
+    """The register-blocked sweep kernel (7 frames per lane, line-aligned pieces, column-pipelined ring) forced on
+    for shapes of every kind: against the oracle, against the lane-per-frame kernel, and bitwise reproducible
+    across grid sizes.  Neighbouring atoms' data must never leak through the masked units of a shared line."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.analysis import timelag_device
+
+    rng = np.random.default_rng(F * 1000 + A + D)
+    X = rng.random((F, A, D)).astype(dtype)
+    m = (1.0 + (rng.random(D) < 0.4)).astype(dtype)
+    path = "f64" if dtype == np.float64 else "f32_timelag"
+    Xd, md = torch.from_numpy(X).cuda(), torch.from_numpy(m).cuda()
+    before = _lib.launch_count()
+    monkeypatch.setenv("SOAP_TL_RB", "1")
+    plain = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1)]
+    weighted = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    fused = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_NORMALIZED_FUSED, 1, mult=md)]
+    monkeypatch.setenv("SOAP_TL_GRID", "3")
+    weighted3 = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    monkeypatch.delenv("SOAP_TL_GRID")
+    assert _lib.launch_count() - before == 4 * 3  # table setup + sweep + finalize per call
+    monkeypatch.setenv("SOAP_TL_RB", "0")
+    old = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    X64 = X.astype(np.float64)
+    Xw = X64 * np.sqrt(m.astype(np.float64))
+    for k, w in enumerate(windows):
+        assert plain[k].shape == (F - w, A)
+        assert_distance_parity(plain[k], O.timeSOAP_batched(X64, window=w, kind=O.KIND_SIMPLE)[0], path, what=f"plain w{w}")
+        want = O.timeSOAP_batched(Xw, window=w, kind=O.KIND_SIMPLE)[0]
+        assert_distance_parity(weighted[k], want, path, what=f"weighted w{w}")
+        assert_distance_parity(weighted[k], old[k], path, what=f"vs lane-per-frame kernel w{w}")
+        assert_distance_parity(fused[k], O.timeSOAP_batched(O.normalizeArray(Xw), window=w, kind=O.KIND_NORMALIZED)[0], path, what=f"fused w{w}")
+        assert_array_equal(weighted[k], weighted3[k])
+    # an atom full of NaN poisons only itself, although it shares its first and last line with its neighbours
+    if A >= 3:
+        Xn = X.copy()
+        Xn[:, 1, :] = np.nan
+        monkeypatch.setenv("SOAP_TL_RB", "1")
+        got = timelag_device(torch.from_numpy(Xn).cuda(), windows[:1], _lib.KIND_SIMPLE, 1, mult=md)[0].cpu().numpy()
+        assert np.isnan(got[:, 1]).all()
+        # (a call with fewer windows may cut the rows into different pieces: same values to rounding, not bitwise)
+        assert_distance_parity(np.delete(got, 1, axis=1), np.delete(weighted[0], 1, axis=1), path, what="NaN neighbour")
+
+
 def test_host_trajectory_larger_than_budget_is_tiled_over_atoms(S, monkeypatch):
     """host inputs that do not fit the device budget are processed in atom tiles (same results)."""
     from cpctools_b200 import analysis
