@@ -359,26 +359,79 @@ def run_gpu_arm(args):
            "host_cpus_bound": None if host_cpus is None else len(host_cpus)}
     del host
 
-    # result collective (reported beside the step, not inside it: results stay sharded by design)
+    # result collective: every rank ends with the full t[F-w, A] of every window.  Timed (a) alone and (b) INSIDE
+    # the step loop, where the gather of step k runs on a side stream under the sweep of step k+1
+    # (`value_with_gather` is the honest whole-job rate when the results are wanted on every rank)
     gather = None
+    parity = None
     if world > 1:
         from cpctools_b200.sharding import gather_columns
 
         ts, _ = out
         full = [gather_columns(t, total_atoms) for t in ts]  # warm-up (NCCL communicator, buffers)
-        del full
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         full = [gather_columns(t, total_atoms) for t in ts]
         g1.record()
         torch.cuda.synchronize()
-        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        gms = _allreduce(dist, world, torch, g0.elapsed_time(g1), dist.ReduceOp.MAX)
         nbytes = sum(int(f.numel()) * 8 for f in full)
-        gather = {"collective": "NCCL all_gather of the t[F-w, A/G] slabs (every rank ends with t[F-w, A])",
-                  "bytes_per_rank_out": nbytes, "ms": float(gms.item()), "GBps_per_rank": nbytes / float(gms.item()) / 1e6}
-        del full
+        gather = {"collective": "NCCL all_gather_into_tensor of the t[F-w, A/G] slabs + one interleaving pass (every rank ends with t[F-w, A])",
+                  "bytes_per_rank_out": nbytes, "ms": gms, "GBps_per_rank": nbytes / gms / 1e6}
+        # (b) overlapped: K steps, each step's slabs gathered on a side stream while the next step computes
+        side = torch.cuda.Stream()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        keep = None
+        for k in range(args.steps):
+            ts_k, dts_k = step()
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                for t in ts_k:
+                    t.record_stream(side)
+                keep = [gather_columns(t, total_atoms) for t in ts_k]
+        torch.cuda.current_stream().wait_stream(side)
+        o1.record()
+        barrier()
+        oms = _allreduce(dist, world, torch, o0.elapsed_time(o1), dist.ReduceOp.MAX)
+        gather["overlapped_ms_per_step"] = oms / args.steps
+        gather["value_with_gather"] = pairs_step * args.steps / (oms * 1e-3)
+        gather["efficiency_vs_no_gather"] = (elapsed_ms / args.steps) / (oms / args.steps)
+        full = keep
+        del keep
+
+        # ---- correctness of what ran under NCCL: (1) every rank recomputes the first atoms of its RIGHT
+        # neighbour's shard from the raw rows (sent over NCCL) and compares with the columns it received in the
+        # gather -- the kernels are deterministic, so this is bitwise; (2) the same atoms through an explicit
+        # torch fp64 expand -> normalise -> distance chain (1e-12 on d^2)
+        ns = min(16, atoms)
+        mine = X[:, :ns, :].contiguous()
+        samples = torch.empty((world, frames, ns, dc), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(samples, mine)
+        nb = (rank + 1) % world
+        per = total_atoms // world
+        redo = timelag_device(samples[nb], WINDOWS, _lib.KIND_SIMPLE, 1, mult=mult)
+        idx = plan.index_device().long()
+        xa = samples[nb][:, :4, :][..., idx]
+        xa = xa / xa.norm(dim=-1, keepdim=True)
+        bitwise, worst, worst_ref = True, 0.0, 0.0
+        for w, t_full, t_redo in zip(WINDOWS, full, redo):
+            got = t_full[:, nb * per : nb * per + ns]
+            bitwise = bitwise and bool(torch.equal(got, t_redo))
+            worst = max(worst, float((got ** 2 - t_redo ** 2).abs().max().item()))
+            ref2 = (2.0 - 2.0 * (xa[w:] * xa[:-w]).sum(-1)).clamp_min(0)
+            worst_ref = max(worst_ref, float((got[:, :4] ** 2 - ref2).abs().max().item()))
+        ok = worst <= 1e-12 and worst_ref <= 1e-12
+        flag = _allreduce(dist, world, torch, 1.0 if ok else 0.0, dist.ReduceOp.MIN)
+        parity = {"timesoap": "ok" if flag == 1.0 else "FAIL", "neighbour_recompute_bitwise": bool(_allreduce(dist, world, torch, 1.0 if bitwise else 0.0, dist.ReduceOp.MIN) == 1.0),
+                  "max_abs_d2_vs_neighbour_recompute": _allreduce(dist, world, torch, worst, dist.ReduceOp.MAX),
+                  "max_abs_d2_vs_torch_f64": _allreduce(dist, world, torch, worst_ref, dist.ReduceOp.MAX),
+                  "sample": f"{ns} atoms x {frames} frames x 4 windows per rank, gathered slab vs recomputation on the neighbour rank"}
+        del full, samples, redo
 
     # single-window calls on the same tile (what one reference call timeSOAP(window=w) costs)
     single = {}
@@ -410,12 +463,45 @@ def run_gpu_arm(args):
     del X, out
     torch.cuda.empty_cache()
 
+    # the same sweep on float32 rows (half the bytes per element, the same shared-memory wavefronts per byte)
+    X32 = torch.empty((frames, atoms, dc), dtype=torch.float32, device="cuda")
+    _lib.check(lib.soap_fill_uniform(X32.data_ptr(), X32.numel(), 12345 + rank, _lib.F32, None), "fill")
+    mult32 = plan.multiplicity_device(torch.float32)
+    for _ in range(2):
+        timelag_device(X32, WINDOWS, _lib.KIND_SIMPLE, 1, mult=mult32)
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)
+    for _ in range(5):
+        timelag_device(X32, WINDOWS, _lib.KIND_SIMPLE, 1, mult=mult32)
+    torch.cuda.synchronize()
+    ms32 = float(np.mean(_lib.profile_read(_lib.PROF_TIMELAG)))
+    _lib.profile_enable(False)
+    nb32 = frames * atoms * dc * 4 + sum((frames - w) * atoms * 8 for w in WINDOWS)
+    roofline_f32 = {"bound": "hbm", "kernel": "timelag_kernel<float,4>", "achieved": nb32 / ms32 / 1e6, "peak": peak, "unit": "GB/s",
+                    "frac": nb32 / ms32 / 1e6 / peak, "kernel_ms": ms32, "algorithmic_bytes_per_launch": nb32,
+                    "pairs_per_s": pairs_per_atom(frames) * atoms / (ms32 * 1e-3), "traffic": None}
+    del X32
+    torch.cuda.empty_cache()
+
+    expand = quippy = None
+    if not args.no_extra:
+        expand = run_expand(args, torch, dist, _lib, S, rank, world, peak)
+        quippy = run_quippy(args, torch, dist, _lib, S, rank, world, peak)
+    tensor_peaks = probe_tensor_peaks(torch) if (rank == 0 and not args.no_allpairs) else None
+    if world > 1:
+        box = [tensor_peaks]
+        dist.broadcast_object_list(box, src=0)
+        tensor_peaks = box[0]
+
     allpairs = None
     if not args.no_allpairs:
-        allpairs = run_allpairs(args, torch, dist, _lib, rank, world)
+        allpairs = run_allpairs(args, torch, dist, _lib, rank, world, tensor_peaks)
+        if parity is not None and allpairs is not None:
+            parity["allpairs"] = allpairs.get("parity")
 
-    cpu_baseline = None
+    cpu_baseline = config1 = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        config1 = run_config1(S)
         raw, sl = cpu_sample(args.ref_frames, args.cpu_atoms)  # ~10 s of single-core work
         t0 = time.perf_counter()
         npairs = cpu_reference_step(raw, sl)
@@ -436,8 +522,9 @@ def run_gpu_arm(args):
                        "frames": frames, "atoms_per_gpu": atoms, "atoms_total": total_atoms, "windows": list(WINDOWS),
                        "pairs_per_step": pairs_step, "l2": "inputs (>= 100 GB per GPU) far larger than the 126 MB L2",
                        "timing": "CUDA events on the launching stream, max over ranks"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "allpairs": allpairs, "result_gather": gather,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_f32": roofline_f32,
+            "cpu_baseline": cpu_baseline, "config1": config1, "expand": expand, "quippy": quippy, "allpairs": allpairs, "tensor_peaks": tensor_peaks,
+            "result_gather": gather, "multi_gpu_parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
@@ -445,7 +532,197 @@ def run_gpu_arm(args):
     return 0
 
 
-def run_allpairs(args, torch, dist, _lib, rank, world):
+def run_config1(S):
+    """BASELINE configs[0], the reference's own CPU-runnable case, in full on both sides: 200 frames x 309 atoms x
+    324 (1 species, nMax = lMax = 8) fp64 -> fillSOAPVectorFromdscribe -> normalizeArray ->
+    timeSOAP(window=1, SOAPdistanceNormalized), numpy in -> numpy out through the public API on the GPU, and
+    the reference algorithm (oracle port) on one host core.  Tiny (fits L2): a parity + latency line."""
+    from oracle import soap_oracle as O
+
+    rng = np.random.default_rng(12345)
+    raw = rng.random((200, 309, 324))
+
+    def gpu():
+        X = S.normalizeArray(S.fillSOAPVectorFromdscribe(raw, 8, 8))
+        return S.timeSOAP(X, window=1, distanceFunction=S.SOAPdistanceNormalized)
+
+    gpu()
+    t0 = time.perf_counter()
+    t_gpu, dt_gpu = gpu()
+    gpu_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    (t_fused, _), = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1,), distanceFunction=S.SOAPdistanceNormalized)
+    fused_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Xo = O.normalizeArray(O.fillSOAPVectorFromdscribe(raw, 8, 8))
+    t_cpu, dt_cpu = O.timeSOAP(Xo, window=1, distanceFunction=O.SOAPdistanceNormalized)
+    cpu_s = time.perf_counter() - t0
+    pairs = t_cpu.size
+    err = float(np.abs(t_gpu ** 2 - t_cpu ** 2).max())
+    err_f = float(np.abs(t_fused ** 2 - t_cpu ** 2).max())
+    return {"workload": "timeSOAP(window=1, SOAPdistanceNormalized) after fill + normalise, 200 frames x 309 atoms x 324 -> 576 fp64 (BASELINE configs[0])",
+            "pairs": int(pairs), "gpu_three_calls_s": gpu_s, "gpu_fused_call_s": fused_s, "cpu_port_s": cpu_s,
+            "gpu_pairs_per_s": pairs / gpu_s, "gpu_fused_pairs_per_s": pairs / fused_s, "cpu_pairs_per_s": pairs / cpu_s,
+            "max_abs_d2_err": err, "max_abs_d2_err_fused": err_f, "shapes": [list(t_gpu.shape), list(dt_gpu.shape)],
+            "parity": "ok" if max(err, err_f) <= 1e-12 and t_gpu.shape == t_cpu.shape and dt_gpu.shape == dt_cpu.shape else "FAIL",
+            "note": "host numpy arrays in and out: the GPU time is launch + PCIe latency, not bandwidth"}
+
+
+def _allreduce(dist, world, torch, value, op):
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=op)
+    return float(t.item())
+
+
+def run_expand(args, torch, dist, _lib, S, rank, world, peak):
+    """BASELINE configs[1]: fillSOAPVectorFromdscribe + normalizeArray fused (one kernel: reads Dc = 1224, writes
+    Df = 1728 per vector) on a device-resident tile of 100 frames x 10 000 atoms -- 1/10 of the 1000 x 10 000
+    dataset, whose input + output (236 GB in fp64) do not fit one GPU together.  Kernel time from CUDA events
+    around expand_kernel; every rank runs its own tile (weak)."""
+    slices, dc = species_slices()
+    plan = S.getExpansionPlan(LMAX, NMAX, SPECIES, slices)
+    frames, atoms = args.expand_frames, args.expand_atoms
+    out = {"workload": f"fused expand+normalise, {frames} frames x {atoms} atoms x Dc {dc} -> Df {plan.d_full}, 2 species",
+           "vectors_per_gpu": frames * atoms, "target_vec_per_s_per_gpu": 1.94e8}
+    for dt, name, code in ((torch.float64, "f64", _lib.F64), (torch.float32, "f32", _lib.F32)):
+        es = 8 if dt == torch.float64 else 4
+        raw = torch.empty((frames, atoms, dc), dtype=dt, device="cuda")
+        _lib.check(_lib.load().soap_fill_uniform(raw.data_ptr(), raw.numel(), 4242 + rank, code, None), "fill")
+        for _ in range(3):
+            full = S.fillAndNormalize(raw, LMAX, NMAX, SPECIES, slices)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        _lib.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            full = S.fillAndNormalize(raw, LMAX, NMAX, SPECIES, slices)
+        e1.record()
+        torch.cuda.synchronize()
+        kms = float(np.mean(_lib.profile_read(_lib.PROF_EXPAND)))
+        _lib.profile_enable(False)
+        ms = _allreduce(dist, world, torch, e0.elapsed_time(e1) / reps, dist.ReduceOp.MAX if world > 1 else None)
+        nvec = frames * atoms
+        nbytes = nvec * (dc + plan.d_full) * es
+        # size-independent properties on the full tile: gather == table lookup (bit-exact up to the norm), unit norms
+        idx = plan.index_device()
+        rows = torch.randint(0, nvec, (4096,), device="cuda")
+        src = raw.reshape(nvec, dc)[rows].double()[:, idx.long()]
+        want = src / src.norm(dim=-1, keepdim=True)
+        err = float((full.reshape(nvec, -1)[rows].double() - want).abs().max().item())
+        out[name] = {"kernel_ms": kms, "ms_per_call": ms, "GBps": nbytes / kms / 1e6, "frac": nbytes / kms / 1e6 / peak,
+                     "vec_per_s_per_gpu": nvec / (kms * 1e-3), "vec_per_s_total": nvec * world / (ms * 1e-3),
+                     "algorithmic_bytes_per_launch": nbytes, "max_abs_err_vs_torch_f64_sample": err,
+                     "parity": "ok" if err <= (1e-12 if es == 8 else 1e-6) else "FAIL"}
+        del raw, full
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_quippy(args, torch, dist, _lib, S, rank, world, peak):
+    """BASELINE configs[4]: raw quippy rows (3 species H/C/O, nMax = lMax = 6: 1197 + 1 columns) -> drop the last
+    column, permute to the dscribe order, expand to 1512, normalise, timeSOAP(window = 1) -- all folded into ONE pass
+    of the time-lag kernel over the raw rows -- in fp64 and in fp32 (the fp64 values rounded), atoms sharded over
+    the ranks; the two precisions are compared (BASELINE: <= 1e-6)."""
+    species = ["H", "C", "O"]
+    frames, atoms = args.quippy_frames, args.quippy_atoms
+    plan = S.getExpansionPlan(6, 6, species, S.utils._quippyContainerSlices(6, 6, species), quippy=True)
+    dq = plan.d_compressed
+    raw = torch.empty((frames, atoms, dq), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().soap_fill_uniform(raw.data_ptr(), raw.numel(), 99 + rank, _lib.F64, None), "fill")
+    out = {"workload": f"raw quippy rows [{frames} x {atoms}/GPU x {dq}] -> permute + expand ({plan.d_full}) + normalise + timeSOAP(window=1), fused",
+           "pairs_per_gpu": (frames - 1) * atoms}
+    res = {}
+    for name, x in (("f64", raw), ("f32", raw.float())):
+        es = x.element_size()
+        fn = lambda: S.timeSOAPfromCompressed(x, 6, 6, species, None, windows=(1,), quippy=True)
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        _lib.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            (t, dt), = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        kms = float(np.mean(_lib.profile_read(_lib.PROF_TIMELAG)))
+        _lib.profile_enable(False)
+        ms = _allreduce(dist, world, torch, e0.elapsed_time(e1) / reps, dist.ReduceOp.MAX if world > 1 else None)
+        nbytes = frames * atoms * dq * es + (frames - 1) * atoms * 8
+        res[name] = t
+        out[name] = {"kernel_ms": kms, "ms_per_call": ms, "GBps": nbytes / kms / 1e6, "frac": nbytes / kms / 1e6 / peak,
+                     "pairs_per_s_total": (frames - 1) * atoms * world / (ms * 1e-3),
+                     "note": None if (dq * es) % 16 == 0 else "rows are not 16-byte multiples: padded once on the device before the kernel (inside ms_per_call, outside kernel_ms)"}
+    d2 = float((res["f32"] ** 2 - res["f64"] ** 2).abs().max().item())
+    big = res["f64"] >= 0.25
+    rel = float(((res["f32"] - res["f64"]).abs() / res["f64"])[big].max().item()) if bool(big.any()) else 0.0
+    d2 = _allreduce(dist, world, torch, d2, dist.ReduceOp.MAX if world > 1 else None)
+    out["fp32_vs_fp64"] = {"max_abs_d2": d2, "max_rel_d_where_d_ge_0.25": rel, "tolerance": 1e-6, "parity": "ok" if d2 <= 1e-6 and rel <= 1e-6 else "FAIL"}
+    # fp64 against torch: a few atoms through the explicit permute -> expand -> normalise -> distance chain
+    idx = plan.index_device().long()
+    xa = raw[:, :4, :][..., idx]
+    xa = xa / xa.norm(dim=-1, keepdim=True)
+    ref2 = 2.0 - 2.0 * (xa[1:] * xa[:-1]).sum(-1)
+    out["f64"]["max_abs_d2_vs_torch"] = float((res["f64"][:, :4] ** 2 - ref2.clamp_min(0)).abs().max().item())
+    del raw, res
+    torch.cuda.empty_cache()
+    return out
+
+
+def probe_tensor_peaks(torch):
+    """The denominators BASELINE.md section 3 left "to measure": dense INT8 (torch._int_mm -> cuBLASLt IMMA), FP64
+    (DGEMM) and TF32 GEMM rates on this GPU, 8192^3, best single call (burst) and a ~1 s back-to-back loop
+    (sustained), CUDA events.  Library GEMMs used ONLY as yardsticks."""
+    out = {}
+    n = 8192
+
+    def rate(fn, flops):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(3, int(1000.0 / best))
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return {"burst": flops / best / 1e9, "sustained": flops * reps / e0.elapsed_time(e1) / 1e9}
+
+    try:
+        a = torch.randint(-100, 100, (n, n), dtype=torch.int8, device="cuda")
+        b = torch.randint(-100, 100, (n, n), dtype=torch.int8, device="cuda").t().contiguous().t()
+        out["int8_tops"] = rate(lambda: torch._int_mm(a, b), 2.0 * n ** 3)
+        del a, b
+    except Exception as e:  # noqa: BLE001
+        out["int8_tops"] = {"error": str(e)[:120]}
+    try:
+        a = torch.randn((n, n), dtype=torch.float64, device="cuda"); b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+        out["fp64_tflops"] = rate(lambda: torch.matmul(a, b), 2.0 * n ** 3)
+        del a, b
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn((n, n), dtype=torch.float32, device="cuda"); b = torch.randn((n, n), dtype=torch.float32, device="cuda")
+        out["tf32_tflops"] = rate(lambda: torch.matmul(a, b), 2.0 * n ** 3)
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        del a, b
+    except Exception as e:  # noqa: BLE001
+        out["gemm_error"] = str(e)[:120]
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_allpairs(args, torch, dist, _lib, rank, world, tensor_peaks=None):
     """BASELINE configs[3]: all-pairs SOAP distance matrix of 200 000 normalised vectors (D = 576),
     row blocks of 25 000 rows per GPU (8 GPUs = the whole 4e10-pair matrix; fewer GPUs = that share of
     it: weak scaling).  The vector set is generated on rank 0 and broadcast over NCCL; the distance
@@ -461,6 +738,10 @@ def run_allpairs(args, torch, dist, _lib, rank, world):
         peaks_json = json.load(open(path))
         bf16 = float(peaks_json["bf16_tflops"])
         bf16_sus = float(peaks_json.get("bf16_tflops_sustained", 0.0)) or None
+    int8_peak = int8_sus = None
+    if tensor_peaks and isinstance(tensor_peaks.get("int8_tops"), dict) and "burst" in tensor_peaks["int8_tops"]:
+        int8_peak, int8_sus = tensor_peaks["int8_tops"]["burst"], tensor_peaks["int8_tops"]["sustained"]
+    parity_ok = True
     for dt, name, nd, kpad in ((torch.float64, "f64", 6, 576), (torch.float32, "f32", 3, 576)):  # K blocks of 64: 576 needs no padding
         X = torch.empty((n_total, dim), dtype=dt, device="cuda")
         if rank == 0:
@@ -487,6 +768,13 @@ def run_allpairs(args, torch, dist, _lib, rank, world):
         _lib.profile_enable(False)
         ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
         chk = block[:64, :4096].double().sum().reshape(1)
+        # a sampled 128 x 4096 tile of THIS rank's block against torch fp64 sqrt|2 - 2 x.y| (d^2 rule of tests/parity.py)
+        xr, xc = X[rows][:128].double(), X[:4096].double()
+        ref2 = (2.0 - 2.0 * (xr @ xc.T)).abs()
+        err2 = float((block[:128, :4096].double() ** 2 - ref2).abs().max().item())
+        tol2 = 1e-12 if dt == torch.float64 else 1e-6
+        err2 = _allreduce(dist, world, torch, err2, dist.ReduceOp.MAX if world > 1 else None)
+        parity_ok = parity_ok and err2 <= tol2
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(chk)
@@ -497,10 +785,14 @@ def run_allpairs(args, torch, dist, _lib, rank, world):
             "value": pairs / (float(ms.item()) * 1e-3), "unit": "pairs/s", "ms_per_step": float(ms.item()),
             "equiv_tflops": 2.0 * pairs * dim / (float(ms.item()) * 1e-3) / 1e12,
             "kernel": f"pairs_i8_kernel<ND={nd}> (tcgen05.mma.kind::i8, {passes} exact digit passes)",
+            "sample_tile_max_abs_d2_err": err2, "sample_tile_tolerance": tol2,
             "roofline": {"bound": "tensor", "achieved": int8_tops, "unit": "TOP/s (int8, executed)",
-                         "peak": None if bf16 is None else 2.0 * bf16,
-                         "frac": None if bf16 is None else int8_tops / (2.0 * bf16),
-                         "peak_source": "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json); int8 dense = 2 x bf16 on sm_100",
+                         "peak": int8_peak if int8_peak else (None if bf16 is None else 2.0 * bf16),
+                         "frac": (int8_tops / int8_peak) if int8_peak else (None if bf16 is None else int8_tops / (2.0 * bf16)),
+                         "peak_source": ("measured in this run: torch._int_mm (cuBLASLt IMMA) 8192^3, best single call" if int8_peak else
+                                         "2 x measured cuBLAS bf16 burst (MEASURED_PEAKS.json); int8 dense = 2 x bf16 on sm_100"),
+                         "peak_int8_sustained": int8_sus, "frac_int8_sustained": (int8_tops / int8_sus) if int8_sus else None,
+                         "peak_bf16x2_proxy": None if bf16 is None else 2.0 * bf16,
                          # the launches are timed back to back inside a long run: the sustained bf16 figure is the
                          # like-for-like denominator, the burst one above the conservative one
                          "peak_sustained": None if bf16_sus is None else 2.0 * bf16_sus,
@@ -532,6 +824,7 @@ def run_allpairs(args, torch, dist, _lib, rank, world):
             del full, Xs
         del X
         torch.cuda.empty_cache()
+    out["parity"] = "ok" if parity_ok else "FAIL"
     return out
 
 
@@ -556,6 +849,11 @@ def main():
     ap.add_argument("--cpu-atoms", type=int, default=150, help="atoms of the cpu_baseline sample inside the GPU arm (~10 s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-allpairs", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the expand (configs[1]) and quippy (configs[4]) objects")
+    ap.add_argument("--expand-frames", type=int, default=100)
+    ap.add_argument("--expand-atoms", type=int, default=10000)
+    ap.add_argument("--quippy-frames", type=int, default=1000)
+    ap.add_argument("--quippy-atoms", type=int, default=4096, help="atoms per GPU of the quippy tile (8 x 4096 on 8 GPUs)")
     ap.add_argument("--allpairs-vectors", type=int, default=200000)
     ap.add_argument("--allpairs-symmetric", type=int, default=50000, help="vectors of the single-GPU symmetric all-pairs call")
     args = ap.parse_args()

@@ -27,6 +27,7 @@ F32, F64 = 0, 1
 KIND_SIMPLE, KIND_KERNEL, KIND_NORMALIZED, KIND_DOT, KIND_COSCLIP, KIND_EUCLID, KIND_NORMALIZED_FUSED = range(7)
 PAIRS_AUTO, PAIRS_SIMT, PAIRS_TENSOR, PAIRS_TENSOR_NATIVE = 0, 1, 2, 3
 MAX_WINDOWS = 4
+NO_EXCLUDE = -(2 ** 63)  # SOAP_NO_EXCLUDE
 
 # every symbol include/soap_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -44,6 +45,9 @@ SIGNATURES = {
     "soap_pairs_scratch_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int]),
     "soap_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_int,
                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "soap_pairs_rowmin_scratch_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "soap_pairs_rowmin": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_int, c_int, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "soap_classify": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p]),
     "soap_transition_counts": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p]),
@@ -51,6 +55,7 @@ SIGNATURES = {
     "soap_residence_events": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                       c_void_p, c_void_p]),
     "soap_copy_rows": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_void_p]),
+    "soap_interleave_shards": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "soap_fill_uniform": (c_int, [c_void_p, c_int64, c_uint64, c_int, c_void_p]),
 }
 

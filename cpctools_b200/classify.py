@@ -100,10 +100,13 @@ def getReferencesFromDataset(dataset) -> SOAPReferences:
     return SOAPReferences(names=attrs["names"].tolist(), spectra=dataset[:], lmax=attrs["lmax"], nmax=attrs["nmax"])
 
 
-def pairs_device(data, spectra, kind: int, power: int = 1, path: int = _lib.PAIRS_AUTO, out=None, want_argmin=False):
+def pairs_device(data, spectra, kind: int, power: int = 1, path: int = _lib.PAIRS_AUTO, out=None, want_argmin=False,
+                 exclude_offset: int = None):
     """Distance matrix of two CUDA tensors ``[M, D]`` x ``[K, D]`` (same float dtype).
 
-    Returns the ``[M, K]`` matrix, or ``(min float64[M], argmin int32[M])`` when ``want_argmin``."""
+    Returns the ``[M, K]`` matrix, or ``(min float64[M], argmin int32[M])`` when ``want_argmin`` (the matrix is then
+    written to ``out`` only if one is given).  Large problems take the tcgen05 path with the minimum fused into its
+    epilogue; ``exclude_offset`` skips column ``i + exclude_offset`` of row ``i`` (the self distance of a row block)."""
     th = _device.require_cuda()
     lib = _lib.load()
     M, D = (int(s) for s in data.shape)
@@ -115,8 +118,21 @@ def pairs_device(data, spectra, kind: int, power: int = 1, path: int = _lib.PAIR
     if want_argmin:
         amin = th.empty(M, dtype=th.float64, device=data.device)
         arg = th.empty(M, dtype=th.int32, device=data.device)
-        if M and K:
-            rc = lib.soap_pairs(data.data_ptr(), spectra.data_ptr(), None, M, K, D, K, kind, int(power), code,
+        tensor = (path != _lib.PAIRS_SIMT and M >= 128 and K >= 256 and M * K >= 1_000_000
+                  and kind in (_lib.KIND_SIMPLE, _lib.KIND_KERNEL, _lib.KIND_NORMALIZED))
+        if exclude_offset is not None and not tensor:
+            raise _lib.SoapB200Error("pairs_device: exclude_offset needs a problem large enough for the tensor-core path")
+        if M and K and tensor:
+            nbytes = lib.soap_pairs_rowmin_scratch_bytes(M, K, D, code)
+            scratch = th.empty(max(int(nbytes), 8), dtype=th.uint8, device=data.device)
+            rc = lib.soap_pairs_rowmin(data.data_ptr(), spectra.data_ptr(), None if out is None else out.data_ptr(), M, K, D,
+                                       K if out is None else int(out.stride(0)), kind, int(power), code,
+                                       _lib.NO_EXCLUDE if exclude_offset is None else int(exclude_offset),
+                                       arg.data_ptr(), amin.data_ptr(), scratch.data_ptr(), stream)
+            _lib.check(rc, "soap_pairs_rowmin")
+        elif M and K:
+            rc = lib.soap_pairs(data.data_ptr(), spectra.data_ptr(), None if out is None else out.data_ptr(), M, K, D,
+                                K if out is None else int(out.stride(0)), kind, int(power), code,
                                 _lib.PAIRS_SIMT, arg.data_ptr(), amin.data_ptr(), None, stream)
             _lib.check(rc, "soap_pairs")
         return amin, arg

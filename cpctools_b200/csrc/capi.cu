@@ -88,9 +88,42 @@ __global__ void fill_uniform_kernel(T *out, long long n, uint64_t seed) {
   }
 }
 
+// out[r][g * width + a] = buf[g][r][a]: turns the [shards][rows][width] buffer an all-gather fills into the
+// [rows][shards * width] array every rank wants (one pass, 128-bit accesses when the width allows)
+__global__ void __launch_bounds__(256) interleave_shards_kernel(const double *__restrict__ buf, double *__restrict__ out,
+                                                               long long shards, long long rows, long long width) {
+  const long long chunks = (width + 1) / 2;  // pairs of doubles
+  const long long total = shards * rows * chunks;
+  const bool vec = (width % 2) == 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i % chunks, gr = i / chunks, r = gr % rows, g = gr / rows;
+    const double *src = buf + (g * rows + r) * width + 2 * c;
+    double *dst = out + (r * shards + g) * width + 2 * c;
+    if (vec) {
+      const int4 v = ldg_stream16(src);
+      stg_stream16(dst, v);
+    } else {
+      dst[0] = src[0];
+      if (2 * c + 1 < width) dst[1] = src[1];
+    }
+  }
+}
+
 }  // namespace soapb
 
 using namespace soapb;
+
+extern "C" int soap_interleave_shards(const double *buf, double *out, int64_t n_shards, int64_t rows, int64_t width,
+                                      void *stream) {
+  SOAP_REQUIRE(n_shards >= 1 && rows >= 0 && width >= 0, "soap_interleave_shards: bad shape");
+  if (rows == 0 || width == 0) return SOAP_OK;
+  SOAP_REQUIRE(buf && out, "soap_interleave_shards: null buffer");
+  SOAP_REQUIRE(width % 2 != 0 || ((reinterpret_cast<uintptr_t>(buf) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "soap_interleave_shards: buffers must be 16-byte aligned");
+  interleave_shards_kernel<<<num_sms() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(buf, out, (long long)n_shards,
+                                                                                        (long long)rows, (long long)width);
+  return check_launch("interleave_shards_kernel");
+}
 
 extern "C" int soap_abi_version(void) { return SOAP_B200_ABI_VERSION; }
 extern "C" const char *soap_last_error(void) { return last_error().c_str(); }

@@ -21,10 +21,13 @@ int pairs_tf32(const float *A, const float *B, float *out, int64_t M, int64_t N,
                int power, void *scratch, cudaStream_t s);
 size_t pairs_tf32_scratch(int64_t M, int64_t N, int D);
 int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
-                 int power, void *scratch, cudaStream_t s);
+                 int power, void *scratch, cudaStream_t s, int32_t *argmin_out = nullptr, double *min_out = nullptr,
+                 long long excl = 0);
 int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
-                 int power, void *scratch, cudaStream_t s);
+                 int power, void *scratch, cudaStream_t s, int32_t *argmin_out = nullptr, double *min_out = nullptr,
+                 long long excl = 0);
 size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype);
+size_t pairs_i8_rowmin_scratch(int64_t M, int64_t N, int D, int dtype);
 
 constexpr int kPT = 64;   // tile edge
 constexpr int kPK = 16;   // k-slab
@@ -173,6 +176,39 @@ extern "C" size_t soap_pairs_scratch_bytes(int64_t n_data, int64_t n_spectra, in
   return pairs_i8_scratch(n_data, n_spectra, dim, dtype);
 }
 
+extern "C" size_t soap_pairs_rowmin_scratch_bytes(int64_t n_data, int64_t n_spectra, int dim, int dtype) {
+  return pairs_i8_rowmin_scratch(n_data, n_spectra, dim, dtype);
+}
+
+// row minima / arg-minima on the tensor-core path (the matrix itself optional)
+static int pairs_rowmin_tensor(const void *data, const void *spectra, void *out, int64_t n_data, int64_t n_spectra, int dim,
+                               int64_t ldo, int kind, int power, int dtype, long long excl, int32_t *argmin_out,
+                               double *min_out, void *scratch, cudaStream_t s) {
+  SOAP_REQUIRE(kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL || kind == SOAP_KIND_NORMALIZED,
+               "soap_pairs: row minima on the tensor-core path exist for the three SOAP distances only (kind %d)", kind);
+  SOAP_REQUIRE(n_spectra < 2147483647LL, "soap_pairs: too many columns for an int32 arg-minimum");
+  SOAP_REQUIRE(scratch != nullptr, "soap_pairs: row minima on the tensor-core path need soap_pairs_rowmin_scratch_bytes() of scratch");
+  if (dtype == SOAP_F64)
+    return pairs_i8_f64(static_cast<const double *>(data), static_cast<const double *>(spectra), static_cast<double *>(out),
+                        n_data, n_spectra, dim, ldo, kind, power, scratch, s, argmin_out, min_out, excl);
+  return pairs_i8_f32(static_cast<const float *>(data), static_cast<const float *>(spectra), static_cast<float *>(out), n_data,
+                      n_spectra, dim, ldo, kind, power, scratch, s, argmin_out, min_out, excl);
+}
+
+extern "C" int soap_pairs_rowmin(const void *data, const void *spectra, void *out, int64_t n_data, int64_t n_spectra, int dim,
+                                 int64_t ldo, int kind, int power, int dtype, int64_t exclude_offset, int32_t *argmin_out,
+                                 double *min_out, void *scratch, void *stream) {
+  SOAP_REQUIRE(n_data >= 0 && n_spectra >= 0 && dim > 0, "soap_pairs_rowmin: bad shape");
+  if (n_data == 0 || n_spectra == 0) return SOAP_OK;
+  SOAP_REQUIRE(data && spectra && (argmin_out || min_out), "soap_pairs_rowmin: null buffer");
+  SOAP_REQUIRE(!out || ldo >= n_spectra, "soap_pairs_rowmin: ldo %lld < n_spectra", (long long)ldo);
+  SOAP_REQUIRE(dtype == SOAP_F32 || dtype == SOAP_F64, "soap_pairs_rowmin: dtype %d", dtype);
+  SOAP_REQUIRE(tensor_eligible(n_data, n_spectra, dim, kind, dtype, SOAP_PAIRS_TENSOR),
+               "soap_pairs_rowmin: shape not eligible for the tensor-core path (>= 128 x 256)");
+  return pairs_rowmin_tensor(data, spectra, out, n_data, n_spectra, dim, ldo, kind, power, dtype, (long long)exclude_offset,
+                             argmin_out, min_out, scratch, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int soap_pairs(const void *data, const void *spectra, void *out, int64_t n_data, int64_t n_spectra,
                           int dim, int64_t ldo, int kind, int power, int dtype, int path, int32_t *argmin_out,
                           double *min_out, void *scratch, void *stream) {
@@ -187,7 +223,7 @@ extern "C" int soap_pairs(const void *data, const void *spectra, void *out, int6
   const bool am = argmin_out || min_out;
   bool tensor = false;
   if (path == SOAP_PAIRS_TENSOR || path == SOAP_PAIRS_TENSOR_NATIVE) {
-    SOAP_REQUIRE(!am, "soap_pairs: argmin/min is only fused on the SIMT path");
+    SOAP_REQUIRE(!am || path == SOAP_PAIRS_TENSOR, "soap_pairs: argmin/min is fused on the SIMT and the int8 tensor path only");
     SOAP_REQUIRE(tensor_eligible(n_data, n_spectra, dim, kind, dtype, path),
                  "soap_pairs: shape/kind not eligible for the tensor-core path (>= 128 x 256; native fp64: even D, "
                  ">= 128 x 128; no EUCLID)");
@@ -206,6 +242,9 @@ extern "C" int soap_pairs(const void *data, const void *spectra, void *out, int6
       return pairs_tf32(static_cast<const float *>(data), static_cast<const float *>(spectra),
                         static_cast<float *>(out), n_data, n_spectra, dim, ldo, kind, power, scratch, s);
     }
+    if (am)  // scratch must then hold soap_pairs_rowmin_scratch_bytes(); no column is excluded
+      return pairs_rowmin_tensor(data, spectra, out, n_data, n_spectra, dim, ldo, kind, power, dtype, SOAP_NO_EXCLUDE,
+                                 argmin_out, min_out, scratch, s);
     if (dtype == SOAP_F64)
       return pairs_i8_f64(static_cast<const double *>(data), static_cast<const double *>(spectra),
                           static_cast<double *>(out), n_data, n_spectra, dim, ldo, kind, power, scratch, s);

@@ -148,13 +148,26 @@ __device__ __forceinline__ void tile_coords_i8(long long t, int tiles_m, int til
   tn = first + (int)(r % width);
 }
 
-template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, bool SYM, int EW, bool COS, typename OutT>
+// numpy.argmin / numpy.amin order for values visited in increasing column order: the first NaN wins, then the
+// smaller value, then the earlier column
+template <typename V>
+__device__ __forceinline__ void am_update(V v, int j, V &bv, int &bj) {
+  if (bj < 0 || (bv == bv && (v != v || v < bv))) bv = v, bj = j;
+}
+
+constexpr int kI8PanelW = 6;        // tile columns per panel (L2 reuse of the B tiles)
+constexpr int kI8MaxPanels = 2048;  // symmetric calls: panel offsets live in shared memory
+
+// AM: also keep, per row and (tile column, epilogue warp), the minimum over the columns and its index
+// (am_val / am_idx [slot][row], slot = tn * (EW / 4) + part; rowmin_reduce_kernel folds the slots); `out` may
+// then be NULL.  Column row + excl is skipped (the self distance of a row block).
+template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, bool SYM, int EW, bool COS, bool AM, typename OutT>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
     pairs_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     OutT *__restrict__ out, const double *__restrict__ sa, const double *__restrict__ sb,
                     const double *__restrict__ uu, const double *__restrict__ vv, long long M, long long N, int KB,
                     long long ldo, int kind, int power, int tiles_m, int tiles_n, int debug_flags,
-                    const int2 *__restrict__ tile_list, long long n_listed) {
+                    double *__restrict__ am_val, int *__restrict__ am_idx, long long excl) {
   constexpr int BM = kI8BM;
   constexpr int kI8EpiWarps = EW;
   constexpr int A_PLANE = BM * BKB, B_PLANE = BN * BKB;
@@ -176,20 +189,49 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
   // FAST epilogues: per-warp [32 rows][64 + 16 pad bytes] tile that turns a chunk of the accumulator
   // (lane = row) into row-contiguous 64-byte stores
   unsigned char *epi_stage = reinterpret_cast<unsigned char *>(col_rn + kI8EpiWarps * BN);
+  // symmetric calls: first tile of every panel in the walk below (after the staging tiles)
+  long long *panel_off = reinterpret_cast<long long *>(epi_stage + (FAST ? kI8EpiWarps * 32 * kI8StagePitch : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // symmetric mode (data is spectra): only tiles that reach the upper triangle are listed, and every
-  // computed value is also written to its mirrored position
+  // symmetric mode (data is spectra): only tiles that reach the upper triangle are computed, and every value is
+  // also written to its mirrored position.  Panels of 6 tile columns are walked row by row (L2 reuse) down to
+  // the last tile row that still touches the upper triangle; (tm, tn) follows from the tile number through the
+  // per-panel offsets -- no tile list, no host work per call.  The few tiles of a panel's last rows that lie
+  // wholly below the diagonal are skipped by every role.
   constexpr bool symmetric = SYM;
-  const long long tiles = symmetric ? n_listed : (long long)tiles_m * tiles_n;
-  auto coords = [&](long long t, int &tm, int &tn) {
-    if (symmetric) {
-      const int2 c = tile_list[t];
-      tm = c.x;
-      tn = c.y;
-    } else {
-      tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
+  const int n_panels = (tiles_n + kI8PanelW - 1) / kI8PanelW;
+  auto panel_rows = [&](int p) {  // tile rows tm with tm * BM < (last column of the panel + 1) * BN
+    const long long last_col = min((long long)(p + 1) * kI8PanelW, (long long)tiles_n) * BN;
+    return (int)min((long long)tiles_m, (last_col + BM - 1) / BM);
+  };
+  if (symmetric) {
+    if (threadIdx.x == 0) {
+      long long acc = 0;
+      for (int p = 0; p < n_panels; ++p) {
+        panel_off[p] = acc;
+        acc += (long long)panel_rows(p) * min(kI8PanelW, tiles_n - p * kI8PanelW);
+      }
+      panel_off[n_panels] = acc;
     }
+    __syncthreads();
+  }
+  const long long tiles = symmetric ? panel_off[n_panels] : (long long)tiles_m * tiles_n;
+  // returns false for a tile that needs no work (symmetric mode: wholly below the diagonal)
+  auto coords = [&](long long t, int &tm, int &tn) -> bool {
+    if (symmetric) {
+      int lo = 0, hi = n_panels - 1;
+      while (lo < hi) {  // last panel whose first tile is <= t
+        const int mid = (lo + hi + 1) >> 1;
+        if (panel_off[mid] <= t) lo = mid; else hi = mid - 1;
+      }
+      const int first = lo * kI8PanelW, width = min(kI8PanelW, tiles_n - first);
+      const long long r = t - panel_off[lo];
+      tm = (int)(r / width);
+      tn = first + (int)(r % width);
+      return (long long)(tn + 1) * BN > (long long)tm * BM;
+    }
+    tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
+    return true;
   };
 
   if (threadIdx.x == 0) {
@@ -220,7 +262,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
       uint32_t ph = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
         int tm, tn;
-        coords(t, tm, tn);
+        if (!coords(t, tm, tn)) continue;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait_guard(&empty[s], ph ^ 1);
           unsigned char *st = smem + (size_t)s * STAGE_BYTES;
@@ -239,9 +281,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      {
+        int tm, tn;
+        if (!coords(t, tm, tn)) continue;
+      }
       const int as = it % ACC;
-      mbar_wait_guard(&tmem_empty[as], (uint32_t)(((it / ACC) & 1) ^ 1));  // epilogue has drained this accumulator set
+      const int it_now = it++;
+      mbar_wait_guard(&tmem_empty[as], (uint32_t)(((it_now / ACC) & 1) ^ 1));  // epilogue has drained this accumulator set
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * ND * BN);
       for (int kb = 0; kb < KB; ++kb) {
@@ -281,10 +328,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
     const bool need_norms = (kind != SOAP_KIND_NORMALIZED);
     constexpr int VEC = 16 / (int)sizeof(OutT);
     const bool vec_ok = ((ldo % VEC) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    int it = 0;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+    int it = -1;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
       int tm, tn;
-      coords(t, tm, tn);
+      if (!coords(t, tm, tn)) continue;
+      ++it;
       const int as = it % ACC;
       if constexpr (FAST) {
         // SOAPdistanceNormalized (distances.py:83) with a lean, kind-specific epilogue.  fp32: entirely in
@@ -343,6 +391,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
         if constexpr (ND == 3) {
           const bool vec4 = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
           const float prow = __int_as_float((min(max(ei - 1023, -126), 127) + 127) << 23);  // used when `lean`
+          float best_v = 0.f;  // AM: running minimum of this lane's row over this warp's chunks of the tile
+          int best_j = -1;
           // one chunk loop, three compile-time flavours of the per-output arithmetic:
           // 0 = lean SOAPdistanceNormalized, 1 = general SOAPdistanceNormalized, 2 = cosine kinds
           auto chunk_loop = [&](auto mode_tag) {
@@ -387,6 +437,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                   }
                 }
               }
+              if constexpr (AM) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const long long col = col0 + j + k4;
+                  if (col < N && col != row + excl) am_update(o[k4], (int)col, best_v, best_j);
+                }
+              }
               *reinterpret_cast<float4 *>(stg + lane * (kI8StagePitch / 4) + j) = make_float4(o[0], o[1], o[2], o[3]);
               if (symmetric && row_ok) {  // out[col][row]: the 32 lanes of a warp write 32 consecutive rows
 #pragma unroll
@@ -395,7 +452,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
               }
             }
             __syncwarp();
-            if (!(debug_flags & 4)) {
+            if (!(debug_flags & 4) && (!AM || out != nullptr)) {
               const int cq = (lane & 3) * 4;
 #pragma unroll
               for (int m = 0; m < 4; ++m) {
@@ -426,6 +483,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
             else
               chunk_loop(std::integral_constant<int, 1>{});
           }
+          if constexpr (AM) {
+            if (row_ok) {
+              const size_t slot = (size_t)tn * PARTS + part;
+              am_val[slot * M + row] = (double)best_v;
+              am_idx[slot * M + row] = best_j;
+            }
+          }
         } else {
           // fp64 SOAPdistanceNormalized: the six digit sums are folded into two exact 64-bit integers,
           // converted once each; the power-of-two scaling is one exact multiply; IEEE sqrt
@@ -433,6 +497,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
           constexpr double kHi = 1.0 / (double)(1ull << (8 * (ND / 2 - 1)));
           constexpr double kLo = 1.0 / (double)(1ull << (8 * (ND - 1)));
           const double prow = __hiloint2double(ei << 20, 0);  // 2^(e_i - 1023), only used when `lean`
+          double best_v = 0.0;
+          int best_j = -1;
 #pragma unroll 1
           for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 8); c += PARTS) {
             uint32_t v[ND][8];
@@ -472,7 +538,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                 o[k2] = cosine ? fast_cosine_distance(tsum * pw, ri * my_rn[c * 8 + jj], kind, power)
                                : sqrt(fabs(fma(-2.0, tsum * pw, 2.0)));
               }
-              if (row_ok) {
+              if constexpr (AM) {
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                  const long long col = col0 + j + k2;
+                  if (col < N && col != row + excl) am_update(o[k2], (int)col, best_v, best_j);
+                }
+              }
+              if (row_ok && (!AM || out != nullptr)) {
                 if (vec2 && col0 + j + 2 <= N) {
                   *reinterpret_cast<double2 *>(dst + j) = make_double2(o[0], o[1]);
                 } else {
@@ -486,6 +559,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                     if (col0 + j + k2 < N) reinterpret_cast<double *>(out)[(size_t)(col0 + j + k2) * ldo + row] = o[k2];
                 }
               }
+            }
+          }
+          if constexpr (AM) {
+            if (row_ok) {
+              const size_t slot = (size_t)tn * PARTS + part;
+              am_val[slot * M + row] = best_v;
+              am_idx[slot * M + row] = best_j;
             }
           }
         }
@@ -576,18 +656,49 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
   }
 }
 
+// folds the per-(tile column, epilogue warp) minima of a row: numpy's order (first NaN, smaller value, smaller index)
+__global__ void __launch_bounds__(256)
+    rowmin_reduce_kernel(const double *__restrict__ val, const int *__restrict__ idx, long long slots, long long M,
+                         int32_t *__restrict__ argmin_out, double *__restrict__ min_out) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  double bv = 0.0;
+  int bj = -1;
+  for (long long sl = 0; sl < slots; ++sl) {
+    const int j = idx[sl * M + row];
+    if (j < 0) continue;
+    const double v = val[sl * M + row];
+    const bool vn = v != v, bn = bv != bv;
+    bool take;
+    if (bj < 0) take = true;
+    else if (vn || bn) take = vn && (!bn || j < bj);
+    else take = v < bv || (v == bv && j < bj);
+    if (take) bv = v, bj = j;
+  }
+  if (argmin_out) argmin_out[row] = bj;
+  if (min_out) min_out[row] = bj < 0 ? __longlong_as_double(0x7ff8000000000000ll) : bv;
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 template <int ND, int BKB>
 static size_t i8_scratch_bytes(int64_t M, int64_t N, int D) {
   const size_t Dp = align_up((size_t)D, BKB);
-  const size_t tiles = ((size_t)(M + kI8BM - 1) / kI8BM) * ((size_t)(N + 31) / 32);  // upper bound on listed tiles
-  return align_up((size_t)ND * M * Dp, 1024) + align_up((size_t)ND * N * Dp, 1024) + (size_t)(M + N) * 16 + 4096 + tiles * 8;
+  return align_up((size_t)ND * M * Dp, 1024) + align_up((size_t)ND * N * Dp, 1024) + (size_t)(M + N) * 16 + 4096;
 }
+// per-(tile column, epilogue warp) row minima of the AM variants: BN >= 80, at most 3 warps per TMEM quarter
+static size_t i8_rowmin_bytes(int64_t M, int64_t N) { return (size_t)((N + 79) / 80) * 3 * (size_t)M * 12 + 256; }
+
+struct I8RowMin {
+  int32_t *argmin_out;
+  double *min_out;
+  long long excl;
+};
 
 template <typename InT, int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, int EW, bool COS, typename OutT>
 static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
-                           int power, void *scratch, cudaStream_t s) {
-  SOAP_REQUIRE(out != nullptr, "soap_pairs: the tensor-core path writes the full matrix (out == NULL)");
+                           int power, void *scratch, cudaStream_t s, const I8RowMin *am = nullptr) {
+  SOAP_REQUIRE(out != nullptr || am != nullptr, "soap_pairs: the tensor-core path writes the full matrix (out == NULL)");
+  SOAP_REQUIRE(am == nullptr || FAST, "soap_pairs: row minima on the tensor-core path exist for the three SOAP distances only");
   SOAP_REQUIRE((int64_t)ND * M < 2147483647LL && (int64_t)ND * N < 2147483647LL, "soap_pairs: too many rows for one call");
   const int Dp = (int)align_up((size_t)D, BKB);
   unsigned char *p = reinterpret_cast<unsigned char *>(align_up(reinterpret_cast<uintptr_t>(scratch), 1024));
@@ -619,36 +730,44 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   long long tiles = (long long)tiles_m * tiles_n;
   // data is spectra: d(i,j) == d(j,i) bit for bit (exact integer sums, commutative scaling), so only
   // the tiles that contain some j >= i are computed and every value is stored twice
-  const int2 *tile_list = nullptr;
-  long long n_listed = 0;
-  if (FAST && same && getenv("SOAP_I8_NO_SYMMETRY") == nullptr) {
-    std::vector<int2> host_list;
-    host_list.reserve((size_t)tiles / 2 + tiles_m + 16);
-    // panels of 6 tile columns walked row by row (L2 reuse), restricted to the upper triangle
-    for (int first = 0; first < tiles_n; first += 6)
-      for (int tm = 0; tm < tiles_m; ++tm)
-        for (int tn = first; tn < first + 6 && tn < tiles_n; ++tn)
-          if ((long long)(tn + 1) * BN > (long long)tm * kI8BM) host_list.push_back(make_int2(tm, tn));
-    n_listed = (long long)host_list.size();
-    int2 *dev_list = reinterpret_cast<int2 *>(p_after);
-    SOAP_CUDA(cudaMemcpyAsync(dev_list, host_list.data(), host_list.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-    SOAP_CUDA(cudaStreamSynchronize(s));  // the host vector dies with this scope
-    tile_list = dev_list;
-    tiles = n_listed;
-  }
+  // (the upper-triangular tile walk is computed on the device from the tile number: no tile list, no host work
+  // and no stream synchronisation per call)
+  const bool sym = FAST && same && am == nullptr && (tiles_n + kI8PanelW - 1) / kI8PanelW <= kI8MaxPanels &&
+                   getenv("SOAP_I8_NO_SYMMETRY") == nullptr;
+  if (sym) tiles = (tiles + 1) / 2 + tiles_m;  // grid sizing only
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   // the reciprocal-norm staging only exists for the cosine kinds (it would not fit beside 4 stages)
   const size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)EW * BN * 4 +
-                      (FAST ? (size_t)EW * (BN * 8 + 32 * kI8StagePitch) : 0);
+                      (FAST ? (size_t)EW * (BN * 8 + 32 * kI8StagePitch) : 0) + (sym ? (size_t)(kI8MaxPanels + 1) * 8 : 0);
   SOAP_REQUIRE(SMEM <= (size_t)max_smem_optin(), "soap_pairs: internal: tile configuration exceeds shared memory");
-  auto kern = tile_list ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, FAST, EW, COS, OutT>
-                        : pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, FAST, false, EW, COS, OutT>;
+  constexpr int PARTS = EW / 4;
+  double *am_val = nullptr;
+  int *am_idx = nullptr;
+  if (am) {
+    am_val = reinterpret_cast<double *>(p_after);
+    am_idx = reinterpret_cast<int *>(am_val + (size_t)tiles_n * PARTS * M);
+  }
+  void (*kern)(CUtensorMap, CUtensorMap, OutT *, const double *, const double *, const double *, const double *, long long,
+               long long, int, long long, int, int, int, int, int, double *, int *, long long);
+  if constexpr (FAST) {
+    kern = am ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, true, false, EW, COS, true, OutT>
+              : (sym ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, true, true, EW, COS, false, OutT>
+                     : pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, true, false, EW, COS, false, OutT>);
+  } else {
+    kern = pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, false, false, EW, COS, false, OutT>;
+  }
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-  ProfScope prof(SOAP_PROF_PAIRS, s);
   const char *dbg = getenv("SOAP_I8_DEBUG");  // experiments: 1 = skip the epilogue, 2 = one MMA per K block, 4 = no stores
-  kern<<<grid, 64 + 32 * EW, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n,
-                                      dbg ? atoi(dbg) : 0, tile_list, n_listed);
-  return check_launch("pairs_i8_kernel");
+  {
+    ProfScope prof(SOAP_PROF_PAIRS, s);
+    kern<<<grid, 64 + 32 * EW, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n,
+                                        dbg ? atoi(dbg) : 0, am_val, am_idx, am ? am->excl : 0);
+    rc = check_launch("pairs_i8_kernel");
+  }
+  if (rc || !am) return rc;
+  rowmin_reduce_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(am_val, am_idx, (long long)tiles_n * PARTS, M, am->argmin_out,
+                                                                 am->min_out);
+  return check_launch("rowmin_reduce_kernel");
 }
 
 size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
@@ -656,21 +775,29 @@ size_t pairs_i8_scratch(int64_t M, int64_t N, int D, int dtype) {
   return dtype == SOAP_F64 ? i8_scratch_bytes<6, 128>(M, N, D) : i8_scratch_bytes<3, 128>(M, N, D);
 }
 
+size_t pairs_i8_rowmin_scratch(int64_t M, int64_t N, int D, int dtype) {
+  return pairs_i8_scratch(M, N, D, dtype) + i8_rowmin_bytes(M, N);
+}
+
 #define I8_LAUNCH(IN, ND, BN, BKB, ACC, ST, FAST, EW, COS, OUT) \
-  launch_pairs_i8<IN, ND, BN, BKB, ACC, ST, FAST, EW, COS, OUT>(A, B, out, M, N, D, ldo, kind, power, scratch, s)
+  launch_pairs_i8<IN, ND, BN, BKB, ACC, ST, FAST, EW, COS, OUT>(A, B, out, M, N, D, ldo, kind, power, scratch, s, am)
 
 // Tile shapes measured on 25 000^2 x 576 (ms, first version of the epilogue), fp32: N160/K64/4 stages 2.19 |
 // N80/K64/4 stages, 2 accumulator sets 2.33 | N160/K128/2 stages 2.35 | N80/K128/2 stages, 2 sets 2.41;
 // fp64: N80/K64/2 stages is the best of N32 (2 sets) / N80 K32 4 stages / N64 3 stages.
 int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
-                 int power, void *scratch, cudaStream_t s) {
+                 int power, void *scratch, cudaStream_t s, int32_t *argmin_out, double *min_out, long long excl) {
+  I8RowMin rm{argmin_out, min_out, excl};
+  const I8RowMin *am = (argmin_out || min_out) ? &rm : nullptr;
   if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, 8, true, float);
   if (kind == SOAP_KIND_NORMALIZED) return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, 8, false, float);
   return I8_LAUNCH(float, 3, 80, 128, 2, 2, false, 8, true, float);
 }
 
 int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
-                 int power, void *scratch, cudaStream_t s) {
+                 int power, void *scratch, cudaStream_t s, int32_t *argmin_out, double *min_out, long long excl) {
+  I8RowMin rm{argmin_out, min_out, excl};
+  const I8RowMin *am = (argmin_out || min_out) ? &rm : nullptr;
   if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, 12, true, double);
   if (kind == SOAP_KIND_NORMALIZED) return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, 12, false, double);
   return I8_LAUNCH(double, 6, 80, 64, 1, 2, false, 8, true, double);

@@ -110,7 +110,7 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
 // U units (16 bytes each) of the lane's frame against the NW lagged frames.  All loads are issued
 // before the first use so that one warp keeps U*(NW+2) shared-memory requests in flight.
 // fp64: exact products accumulated by DFMA, separate chains for the two halves of a unit.
-template <int NW, int U, bool EUCLID, bool HM>
+template <int NW, int U, bool EUCLID, bool HM, bool CLEAN = false>
 __device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
                                                 uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
   double2 m[U], x[U], y[NW][U];
@@ -120,6 +120,18 @@ __device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr
     x[j] = lds_d2(x_addr + off + j * ustep);
 #pragma unroll
     for (int k = 0; k < NW; ++k) y[k][j] = lds_d2(y_addr[k] + off + j * ustep);
+  }
+  if (CLEAN) {  // foreign elements (multiplicity 0) of a row's first / last unit must not leak as 0 * NaN
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      x[j].x = m[j].x != 0.0 ? x[j].x : 0.0;
+      x[j].y = m[j].y != 0.0 ? x[j].y : 0.0;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        y[k][j].x = m[j].x != 0.0 ? y[k][j].x : 0.0;
+        y[k][j].y = m[j].y != 0.0 ? y[k][j].y : 0.0;
+      }
+    }
   }
 #pragma unroll
   for (int j = 0; j < U; ++j) {
@@ -142,7 +154,7 @@ __device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr
 
 // fp32 data: products and a chain of 4*U terms in fp32, chain sums promoted to double (one
 // conversion per 4*U products; the fp32 rounding is bounded to one short chain).
-template <int NW, int U, bool EUCLID, bool HM>
+template <int NW, int U, bool EUCLID, bool HM, bool CLEAN = false>
 __device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
                                                 uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
   float4 m[U], x[U], y[NW][U];
@@ -152,6 +164,22 @@ __device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr
     x[j] = lds_f4(x_addr + off + j * ustep);
 #pragma unroll
     for (int k = 0; k < NW; ++k) y[k][j] = lds_f4(y_addr[k] + off + j * ustep);
+  }
+  if (CLEAN) {  // foreign elements (multiplicity 0) of a row's first / last unit must not leak as 0 * NaN
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      x[j].x = m[j].x != 0.f ? x[j].x : 0.f;
+      x[j].y = m[j].y != 0.f ? x[j].y : 0.f;
+      x[j].z = m[j].z != 0.f ? x[j].z : 0.f;
+      x[j].w = m[j].w != 0.f ? x[j].w : 0.f;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        y[k][j].x = m[j].x != 0.f ? y[k][j].x : 0.f;
+        y[k][j].y = m[j].y != 0.f ? y[k][j].y : 0.f;
+        y[k][j].z = m[j].z != 0.f ? y[k][j].z : 0.f;
+        y[k][j].w = m[j].w != 0.f ? y[k][j].w : 0.f;
+      }
+    }
   }
   float c0 = 0.f, c1 = 0.f;
 #pragma unroll
@@ -186,13 +214,13 @@ __device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr
   }
 }
 
-template <typename T, int NW, int U, bool EUCLID, bool HM>
+template <typename T, int NW, int U, bool EUCLID, bool HM, bool CLEAN = false>
 __device__ __forceinline__ void accum_units(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
                                             uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
   if constexpr (sizeof(T) == 8)
-    accum_units_f64<NW, U, EUCLID, HM>(m_addr, x_addr, y_addr, off, ustep, acc);
+    accum_units_f64<NW, U, EUCLID, HM, CLEAN>(m_addr, x_addr, y_addr, off, ustep, acc);
   else
-    accum_units_f32<NW, U, EUCLID, HM>(m_addr, x_addr, y_addr, off, ustep, acc);
+    accum_units_f32<NW, U, EUCLID, HM, CLEAN>(m_addr, x_addr, y_addr, off, ustep, acc);
 }
 
 // Warp roles: warps 0..CW-1 consume (lane = frame), warp CW produces (TMA / cp.async), warp CW+1 reduces
@@ -208,6 +236,8 @@ __device__ __forceinline__ void accum_units(uint32_t m_addr, uint32_t x_addr, co
 struct TlItem {
   long long a;
   int p, e0, pe, punits;
+  int lead;       // shifted rows: elements of the PREVIOUS row in front of this one (the box starts 16-byte aligned)
+  long long w0;   // first 8-byte word of the piece in the frame row (TMA coordinate)
 };
 
 // per-CTA accumulator traffic: keep the lines in L2 (evict_last) and out of L1 -- between a store and the
@@ -230,8 +260,12 @@ __device__ __forceinline__ double ld_acc(const double *p, uint64_t pol) {
 // consecutive items of the same CTA, so that the reducer can add the pieces up before anything goes to DRAM.
 // Otherwise (few atoms: fewer atoms than would keep every SM busy) items (atom, piece) are dealt round robin
 // and every piece writes its own partial sums, which the finalize kernel adds.
+// `shifted` (rows of 8 mod 16 bytes): the TMA engine wants 16-byte aligned box rows, so the window of an atom whose
+// row starts on an odd 8-byte word begins one word EARLIER; its first unit then carries `lead` foreign elements, or
+// its last unit ends with foreign elements.  The multiplicity table has one variant per shift, zero on the foreign
+// elements, and the consumers clean those units (CLEAN).
 template <int UE>
-__device__ __forceinline__ TlItem tl_item(int j, int split, int upp, int D, bool atom_major) {
+__device__ __forceinline__ TlItem tl_item(int j, int split, int upp, int D, bool atom_major, bool shifted = false) {
   TlItem it;
   if (atom_major) {
     const int k = j / split;
@@ -242,9 +276,13 @@ __device__ __forceinline__ TlItem tl_item(int j, int split, int upp, int D, bool
     it.a = i / split;
     it.p = (int)(i - it.a * split);
   }
-  it.e0 = it.p * upp * UE;
-  it.pe = min(D - it.e0, upp * UE);  // elements of this piece (> 0)
-  it.punits = (it.pe + UE - 1) / UE;
+  constexpr int ES = 16 / UE;
+  const long long sw = it.a * D * ES / 8;  // first word of the row (rows are whole words on this path)
+  it.lead = (shifted && (sw & 1)) ? 8 / ES : 0;
+  it.e0 = it.p * upp * UE;                       // relative to the (aligned) window
+  it.pe = min(it.lead + D - it.e0, upp * UE);    // elements of this piece; <= 0 for an empty last piece
+  it.punits = it.pe > 0 ? (it.pe + UE - 1) / UE : 0;
+  it.w0 = sw - (it.lead ? 1 : 0) + (long long)it.e0 * ES / 8;
   return it;
 }
 
@@ -253,7 +291,7 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
     timelag_kernel(const T *__restrict__ X, const T *__restrict__ mult, double *__restrict__ sums,
                    double *__restrict__ cta_acc,
                    long long F, long long A, int D, int split, int upp, int stride, int R, int lag_blocks,
-                   int mbuf, int4 win4, int bulk_ok, const __grid_constant__ CUtensorMap tmap) {
+                   int mbuf, int4 win4, int bulk_ok, int mult_pitch, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int UE = 16 / (int)sizeof(T);
   constexpr int Q = NW + 1;
@@ -303,9 +341,11 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
     const int back = nslots - lag_blocks;
     int s = 0, js = 0, jph = 0, g = 0;
     for (int k = 0; k < n_my; ++k) {
-      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major);
+      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major, (bulk_ok & 32) != 0);
       const T *xa = X + (size_t)it.a * D + it.e0;
       const int mslot = k & (mbuf - 1);
+      // shifted rows: one multiplicity table per shift ([2][mult_pitch] elements)
+      const T *mrow = mult + ((bulk_ok & 32) && it.lead ? mult_pitch : 0) + it.e0;
       for (int b = 0; b < nblk; ++b, ++g) {
         if (g >= back) {
           mbar_wait(&empty[js], (uint32_t)jph);
@@ -319,11 +359,10 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
           // zero-filled and still counted in the transaction bytes); the item's multiplicities ride on
           // the barrier of its first block
           if (lane == 0) {
-            const uint32_t mbytes = (HAS_MULT && b == 0) ? (uint32_t)it.pe * (uint32_t)sizeof(T) : 0u;
+            const uint32_t mbytes = (HAS_MULT && b == 0) ? (uint32_t)it.punits * 16u : 0u;  // (padded with zeros by the host side)
             mbar_expect_tx(&full[s], (uint32_t)kBlk * (uint32_t)stride + mbytes);
-            tma_load_2d(ring + (size_t)s * kBlk * stride, &tmap, (int)(((size_t)it.a * D + it.e0) * sizeof(T) / 8),
-                        (int)f0, &full[s]);
-            if (mbytes) bulk_g2s(msm + (size_t)mslot * upp * 16, mult + it.e0, mbytes, &full[s]);
+            tma_load_2d(ring + (size_t)s * kBlk * stride, &tmap, (int)it.w0, (int)f0, &full[s]);
+            if (mbytes) bulk_g2s(msm + (size_t)mslot * upp * 16, mrow, mbytes, &full[s]);
           }
         } else {
           const int nf = (int)min((long long)kBlk, F - f0);
@@ -349,7 +388,7 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
     int g = 0;
     const uint64_t pol = l2_policy_evict_last();
     for (int k = 0; k < n_my; ++k) {
-      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major);
+      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major, (bulk_ok & 32) != 0);
       // pieces 0 .. split-2 leave their running sums in this CTA's accumulator (read back by the same lane for
       // the next piece: L2 traffic only), the last piece writes the totals of the atom
       double *srow = atom_major ? sums + (size_t)it.a * Q * (size_t)F : sums + ((size_t)it.a * split + it.p) * Q * (size_t)F;
@@ -387,8 +426,14 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
     for (int k = 0; k < NW; ++k) wmod[k] = win[k] % R;
     int s = 0, ph = 0, g = 0;
     for (int k = 0; k < n_my; ++k) {
-      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major);
-      const int my_units = it.punits > warp ? (it.punits - warp + CW - 1) / CW : 0;
+      const TlItem it = tl_item<UE>(k, split, upp, D, atom_major, (bulk_ok & 32) != 0);
+      int my_units = it.punits > warp ? (it.punits - warp + CW - 1) / CW : 0;
+      // shifted rows: the unit that starts with the previous row's elements (first unit of piece 0 = warp 0's
+      // first) and the unit that ends with the next row's (the last one) are taken separately, cleaned
+      const bool head = HAS_MULT && (bulk_ok & 32) && it.lead != 0 && it.p == 0 && warp == 0 && my_units > 0;
+      const bool tail = HAS_MULT && (bulk_ok & 32) && it.pe > 0 && (it.pe % UE) != 0 && (it.punits - 1) % CW == warp &&
+                        !(head && my_units == 1);
+      if (tail) --my_units;
       const uint32_t m_addr = msm_addr + (uint32_t)(k & (mbuf - 1)) * upp * 16;
       for (int b = 0; b < nblk; ++b, ++g) {
         const int slot = s * kBlk + lane;  // ring slot of this lane's frame (R is a multiple of 32)
@@ -405,6 +450,10 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
         for (int q = 0; q < 2 * Q; ++q) acc[q] = 0.0;
         mbar_wait(&full[s], (uint32_t)ph);
         int n = 0;
+        if (head) {
+          accum_units<T, NW, 1, EUCLID, HAS_MULT, true>(m_addr, x_addr, y_addr, off0, ustep, acc);
+          n = 1;
+        }
         if (bulk_ok & 4) n = my_units;  // diagnostic: no accumulation
         for (; n + UB <= my_units; n += UB)
           accum_units<T, NW, UB, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
@@ -422,6 +471,8 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
         }
         if (n < my_units)
           accum_units<T, NW, 1, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+        if (tail && !(bulk_ok & 4))
+          accum_units<T, NW, 1, EUCLID, HAS_MULT, true>(m_addr, x_addr, y_addr, off0 + my_units * ustep, ustep, acc);
         // hand the partial sums to the reducer (it is ~10x faster than a block: this wait is free)
         if (g >= 1) mbar_wait(red_empty, (uint32_t)((g - 1) & 1));
         double *r = red + (size_t)warp * Q * 32;
@@ -602,9 +653,19 @@ static int dispatch_timelag_rb(const void *X, const void *mult, double *scratch,
   return set_error(SOAP_EINVAL, "soap_timelag: no register-blocked variant for %d + %d windows", ch.ns, ch.nl);
 }
 
+// shifted rows: table[ph][i] = multiplicity of element i - ph * lead of the row (ones when the caller passes none),
+// zero outside the row -- what masks the foreign elements of the first / last unit of an atom's window
+template <typename T>
+__global__ void shift_mult_kernel(const T *__restrict__ mult, T *__restrict__ out, int D, int pitch, int lead) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * pitch; i += gridDim.x * blockDim.x) {
+    const int ph = i / pitch, e = i - ph * pitch - ph * lead;
+    out[i] = (e >= 0 && e < D) ? (mult ? mult[e] : (T)1) : (T)0;
+  }
+}
+
 template <typename T, int NW, bool HM>
 static int launch_timelag(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D,
-                          const TimelagPlan &pl, const int *w, int kind, int bulk_ok, cudaStream_t s) {
+                          const TimelagPlan &pl, const int *w, int kind, int bulk_ok, int mult_pitch, cudaStream_t s) {
   const int4 win4 = make_int4(w[0], NW > 1 ? w[1] : 0, NW > 2 ? w[2] : 0, NW > 3 ? w[3] : 0);
   auto kern = (kind == SOAP_KIND_EUCLID) ? timelag_kernel<T, NW, true, HM, kTlWarps, 4>
                                          : timelag_kernel<T, NW, false, HM, kTlWarps, 4>;
@@ -652,7 +713,7 @@ static int launch_timelag(const void *X, const void *mult, double *scratch, int6
   ProfScope prof(SOAP_PROF_TIMELAG, s);
   kern<<<(unsigned)grid, threads, pl.smem, s>>>(static_cast<const T *>(X), static_cast<const T *>(mult), scratch, cta_acc,
                                                 (long long)F, (long long)A, D, pl.split, pl.upp, pl.stride, pl.R,
-                                                (pl.max_lag + kBlk - 1) / kBlk, pl.mbuf, win4, bulk_ok, tmap);
+                                                (pl.max_lag + kBlk - 1) / kBlk, pl.mbuf, win4, bulk_ok, mult_pitch, tmap);
   return check_launch("timelag_kernel");
 }
 
@@ -670,6 +731,9 @@ static int launch_finalize(const double *scratch, double *t, const int64_t *off,
 }  // namespace soapb
 
 using namespace soapb;
+
+// room at the end of the scratch area for the zero-padded multiplicities (rows that are not whole units)
+static size_t tl_pad_bytes(int dim, int es) { return 2 * ((size_t)dim + 32) * es + 256; }
 
 static int check_windows(int64_t F, const int *w, int nw, const char *who) {
   SOAP_REQUIRE(w != nullptr && nw >= 1 && nw <= SOAP_MAX_WINDOWS, "%s: 1..%d windows per call", who, SOAP_MAX_WINDOWS);
@@ -694,13 +758,14 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
                8 * rp.mult_elems * es + 256;
   }
   TimelagPlan pl;
-  if (!make_plan(n_frames, dim, es, windows_host, n_windows, pl)) return rb_bytes;
+  const int plan_dim = (((size_t)dim * es) % 16 != 0 && ((size_t)dim * es) % 8 == 0) ? dim + 8 / es : dim;  // shifted rows
+  if (!make_plan(n_frames, plan_dim, es, windows_host, n_windows, pl)) return rb_bytes + tl_pad_bytes(dim, es);
   // totals sums[a][q][f] + one accumulator [q][frames padded to 32] per resident CTA
   const size_t padded = (size_t)((n_frames + kBlk - 1) / kBlk) * kBlk;
   size_t bytes = tl_atom_major(n_atoms)
                      ? ((size_t)n_atoms * pl.Q * (size_t)n_frames + (size_t)tl_max_grid() * pl.Q * padded) * sizeof(double)
                      : (size_t)n_atoms * pl.split * pl.Q * (size_t)n_frames * sizeof(double);
-  return bytes > rb_bytes ? bytes : rb_bytes;
+  return (bytes > rb_bytes ? bytes : rb_bytes) + tl_pad_bytes(dim, es);
 }
 
 extern "C" int soap_timelag(const void *X, const void *mult, double *t, const int64_t *t_offsets_host,
@@ -713,11 +778,31 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
   int rc = check_windows(n_frames, windows_host, n_windows, "soap_timelag");
   if (rc) return rc;
   const int es = dtype == SOAP_F64 ? 8 : 4;
-  // TMA path: 16-byte aligned base pointers and rows that are whole 16-byte units
-  int bulk_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (((size_t)dim * es) % 16 == 0) &&
-                ((reinterpret_cast<uintptr_t>(mult) & 15) == 0);
+  // TMA path: 16-byte aligned base pointers, rows of whole 8-byte words and frames of whole 16-byte units (the
+  // tensor map counts 8-byte words; a row that ends in half a unit -- fp32, D = 4k + 2 -- has that unit masked)
+  const bool whole_units = ((size_t)dim * es) % 16 == 0;
+  int bulk_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (((size_t)dim * es) % 8 == 0) &&
+                (((size_t)n_atoms * dim * es) % 16 == 0) && ((reinterpret_cast<uintptr_t>(mult) & 15) == 0);
   auto s = static_cast<cudaStream_t>(stream);
   auto sc = static_cast<double *>(scratch);
+  int mult_pitch = 0, plan_dim = dim;
+  if (bulk_ok && !whole_units) {
+    // rows of 8 mod 16 bytes: every other atom's window starts one word early (tl_item); the plan covers the
+    // widest window, the multiplicities become a [2][pitch] table that is zero on the foreign elements
+    const int lead = 8 / es, ue = 16 / es;
+    plan_dim = dim + lead;
+    mult_pitch = (plan_dim + ue - 1) / ue * ue + 4 * ue;
+    const size_t total = soap_timelag_scratch_bytes(n_frames, n_atoms, dim, dtype, windows_host, n_windows);
+    void *table = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(static_cast<char *>(scratch) + total - tl_pad_bytes(dim, es)) + 127) & ~(uintptr_t)127);
+    if (dtype == SOAP_F64)
+      shift_mult_kernel<double><<<8, 256, 0, s>>>(static_cast<const double *>(mult), static_cast<double *>(table), dim, mult_pitch, lead);
+    else
+      shift_mult_kernel<float><<<8, 256, 0, s>>>(static_cast<const float *>(mult), static_cast<float *>(table), dim, mult_pitch, lead);
+    rc = check_launch("shift_mult_kernel");
+    if (rc) return rc;
+    mult = table;
+    bulk_ok |= 32;
+  }
   {
     const RbChoice ch = rb_choose(n_frames, n_atoms, dim, es, windows_host, n_windows, kind, bulk_ok != 0);
     RbPlan rp;
@@ -736,13 +821,13 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
     }
   }
   TimelagPlan pl;
-  if (!make_plan(n_frames, dim, es, windows_host, n_windows, pl))
+  if (!make_plan(n_frames, plan_dim, es, windows_host, n_windows, pl))
     return set_error(SOAP_EUNSUPPORTED, "soap_timelag: window %d needs more shared memory than one SM has", pl.max_lag);
   if (bulk_ok) bulk_ok |= env_int("SOAP_TL_DIAG", 0) & 30;
 #define TL_CASE(T, NW)                                                                                          \
   case NW:                                                                                                      \
-    rc = mult ? launch_timelag<T, NW, true>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, s)  \
-              : launch_timelag<T, NW, false>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, s); \
+    rc = mult ? launch_timelag<T, NW, true>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, mult_pitch, s)  \
+              : launch_timelag<T, NW, false>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, mult_pitch, s); \
     if (rc) return rc;                                                                                          \
     return launch_finalize<NW>(sc, t, t_offsets_host, n_frames, n_atoms, tl_atom_major(n_atoms) ? 1 : pl.split, windows_host, kind, power, s);
   if (dtype == SOAP_F64) {

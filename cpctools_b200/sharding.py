@@ -48,6 +48,19 @@ def gather_columns(local, n_total: int, group=None):
     rank, world = _world(group)
     if world == 1:
         return local
+    if (n_total % world == 0 and local.is_cuda and local.dtype == torch.float64 and local.dim() == 2
+            and local.shape[-1] * world == n_total):
+        # equal shards on the GPU: ONE all_gather_into_tensor into [G, rows, A/G] (no padding, no list of
+        # tensors, no cat) and one interleaving pass of libsoapb200 into the [rows, A] layout
+        from . import _device, _lib
+
+        rows, width = int(local.shape[0]), int(local.shape[1])
+        buf = torch.empty((world, rows, width), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(buf, local.contiguous(), group=group)
+        out = torch.empty((rows, n_total), dtype=local.dtype, device=local.device)
+        _lib.check(_lib.load().soap_interleave_shards(buf.data_ptr(), out.data_ptr(), world, rows, width, _device.stream_ptr()),
+                   "soap_interleave_shards")
+        return out
     widest = shard_range(n_total, 0, world)
     width = widest.stop - widest.start
     padded = local.new_zeros(local.shape[:-1] + (width,))
@@ -91,22 +104,33 @@ def time_soap_sharded(trajectory, windows: Sequence[int], compute: Callable, n_a
     return [gather_columns(t, n_atoms_total, group) for t in local]
 
 
-def all_pairs_row_block(vectors, compute: Callable, group=None):
+def all_pairs_row_block(vectors, compute: Callable, group=None, rowmin: Callable = None):
     """Row-block sharded all-pairs matrix: rank r computes ``compute(vectors[rows_r], vectors)``
     (``[n_r, N]``, kept on the rank) and the row-wise minimum over OTHER vectors, its arg-minimum
-    and a checksum, which ARE gathered.  Returns ``(block, rows, row_min[N], row_argmin[N], checksum)``."""
+    and a checksum, which ARE gathered.  Returns ``(block, rows, row_min[N], row_argmin[N], checksum)``.
+
+    ``rowmin(vectors[rows_r], vectors, first_row) -> (min[n_r], argmin[n_r])`` is the fused form (the tcgen05
+    epilogue keeps the minima, e.g. ``pairs_device(..., want_argmin=True, exclude_offset=first_row)``): with it
+    the block is neither copied nor -- when ``compute`` is ``None`` -- ever materialised (320 GB at 200 000
+    vectors); the checksum is then the sum of the row minima.  Without it the minima come from a masked copy of
+    the block (the CPU / gloo route of the tests)."""
     rank, world = _world(group)
     n = int(vectors.shape[0])
     rows = shard_range(n, rank, world)
-    block = compute(vectors[rows], vectors)
-    masked = block.clone()
-    idx = torch.arange(rows.start, rows.stop, device=block.device)
-    masked[torch.arange(idx.numel(), device=block.device), idx] = float("inf")  # drop the self distance
-    masked = torch.nan_to_num(masked, nan=float("inf"))
-    local_min, local_arg = masked.min(dim=1)
+    block = compute(vectors[rows], vectors) if compute is not None else None
+    if rowmin is not None:
+        local_min, local_arg = rowmin(vectors[rows], vectors, rows.start)
+        local_arg = local_arg.to(torch.int64)
+    else:
+        masked = block.clone()
+        idx = torch.arange(rows.start, rows.stop, device=block.device)
+        masked[torch.arange(idx.numel(), device=block.device), idx] = float("inf")  # drop the self distance
+        masked = torch.nan_to_num(masked, nan=float("inf"))
+        local_min, local_arg = masked.min(dim=1)
     row_min = gather_rows(local_min, n, group)
     row_arg = gather_rows(local_arg, n, group)
-    checksum = torch.nan_to_num(block.double(), nan=0.0).sum().reshape(1)
+    source = block if block is not None else local_min
+    checksum = torch.nan_to_num(source.double(), nan=0.0).sum().reshape(1)
     if world > 1:
         dist.all_reduce(checksum, group=group)
     return block, rows, row_min, row_arg, float(checksum.item())

@@ -114,9 +114,23 @@ int soap_diff_transposed(const double *t, double *dt, int64_t rows, int64_t n_at
  * SOAP_PAIRS_TENSOR_NATIVE = native-format tensor GEMM (fp64: DMMA; fp32: tcgen05 3xTF32, whose
  * fp32 round-toward-zero accumulation limits it to ~2e-5 on d^2).
  * If argmin_out / min_out are non-NULL the row-wise argmin (int32) / min (double) over j is
- * produced as well (applyClassification, classify.py:274-275) and `out` may be NULL.
+ * produced as well (applyClassification, classify.py:274-275) and `out` may be NULL
+ * (SOAP_PAIRS_SIMT, SOAP_PAIRS_TENSOR or SOAP_PAIRS_AUTO, which then takes the SIMT kernel).
  */
 enum { SOAP_PAIRS_AUTO = 0, SOAP_PAIRS_SIMT = 1, SOAP_PAIRS_TENSOR = 2, SOAP_PAIRS_TENSOR_NATIVE = 3 };
+/* With path == SOAP_PAIRS_TENSOR the arg-minimum / minimum are fused into the tcgen05 epilogue as well (the three
+ * SOAP distances): every (tile column, epilogue warp) keeps the minimum of its columns per row, a second small kernel
+ * folds them with numpy's rules (first NaN, smaller value, smaller index).  `scratch` must then be
+ * soap_pairs_rowmin_scratch_bytes() large and `out` may be NULL (nothing of the matrix is written).
+ * soap_pairs_rowmin() is that call with one more argument: column j == i + exclude_offset is skipped -- the self
+ * distance when data is the row block [r0, r0 + n_data) of spectra (exclude_offset = r0; SOAP_NO_EXCLUDE for none):
+ * the nearest OTHER vector of every row of the all-pairs matrix without materialising it.
+ */
+#define SOAP_NO_EXCLUDE INT64_MIN
+size_t soap_pairs_rowmin_scratch_bytes(int64_t n_data, int64_t n_spectra, int dim, int dtype);
+int soap_pairs_rowmin(const void *data, const void *spectra, void *out, int64_t n_data, int64_t n_spectra, int dim,
+                      int64_t ldo, int kind, int power, int dtype, int64_t exclude_offset, int32_t *argmin_out,
+                      double *min_out, void *scratch, void *stream);
 size_t soap_pairs_scratch_bytes(int64_t n_data, int64_t n_spectra, int dim, int dtype, int path);
 int soap_pairs(const void *data, const void *spectra, void *out, int64_t n_data, int64_t n_spectra,
                int dim, int64_t ldo, int kind, int power, int dtype, int path, int32_t *argmin_out,
@@ -162,6 +176,12 @@ int soap_residence_events(const int32_t *states, int64_t n_frames, int64_t n_ato
  */
 int soap_copy_rows(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes, size_t rows,
                    int to_device, void *stream);
+
+/* ---- result gather: NCCL all-gathers the ranks' t[F-w][A/G] slabs into
+ * buf[G][rows][width]; this turns them into the out[rows][G * width] array of the reference layout
+ * (timedSOAP[frame][atom], src/SOAPify/analysis.py:53) in one pass.
+ */
+int soap_interleave_shards(const double *buf, double *out, int64_t n_shards, int64_t rows, int64_t width, void *stream);
 
 /* ---- synthetic data for the benchmarks (counter-based hash RNG, reproducible) ------------
  * fills n elements of `dtype` with uniform [0,1) values derived from (seed, element index).

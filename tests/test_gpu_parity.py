@@ -281,6 +281,8 @@ def test_timesoap_sweep_from_compressed_vs_oracle(S, F, A, species, dtype, windo
         (97, 160, 1224, np.float64, (1, 5, 10, 50)),  # rows split into pieces, pieces change inside a CTA
         (60, 640, 1224, np.float64, (1, 5, 10, 50)),  # enough atoms for the atom-major mode: pieces summed on chip
         (41, 601, 612, np.float32, (2, 40)),
+        (64, 450, 1198, np.float32, (1, 5, 10, 50)),  # raw quippy fp32 rows: 8- but not 16-byte multiples, TMA + masked tail unit
+        (40, 6, 6, np.float32, (1, 3)),       # the same with rows shorter than two units
         (35, 5, 7, np.float64, (2, 4)),       # unaligned rows: element-copy path, several items per CTA
         (35, 300, 7, np.float32, (1, 9)),
     ],
@@ -373,6 +375,26 @@ def test_timelag_register_blocked_kernel(S, F, A, D, dtype, windows, monkeypatch
         assert np.isnan(got[:, 1]).all()
         # (a call with fewer windows may cut the rows into different pieces: same values to rounding, not bitwise)
         assert_distance_parity(np.delete(got, 1, axis=1), np.delete(weighted[0], 1, axis=1), path, what="NaN neighbour")
+
+
+def test_timelag_rows_ending_in_half_a_unit_do_not_leak_the_next_row(S):
+    """fp32 rows of 4k + 2 floats (raw quippy: 1198) go through the TMA path with the last 16-byte unit half
+    foreign: a NaN / huge neighbour must not change an atom's result (and poisons only itself)."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.analysis import timelag_device
+
+    rng = np.random.default_rng(5)
+    X = rng.random((50, 8, 1198)).astype(np.float32)
+    base = [t.cpu().numpy() for t in timelag_device(torch.from_numpy(X).cuda(), (1, 7), _lib.KIND_SIMPLE, 1)]
+    for w, t in zip((1, 7), base):
+        assert_distance_parity(t, O.timeSOAP_batched(X.astype(np.float64), window=w, kind=O.KIND_SIMPLE)[0], "f32_timelag")
+    Xn = X.copy()
+    Xn[:, 3, :] = np.nan
+    got = [t.cpu().numpy() for t in timelag_device(torch.from_numpy(Xn).cuda(), (1, 7), _lib.KIND_SIMPLE, 1)]
+    for b, g in zip(base, got):
+        assert np.isnan(g[:, 3]).all()
+        assert_array_equal(np.delete(g, 3, axis=1), np.delete(b, 3, axis=1))
 
 
 def test_host_trajectory_larger_than_budget_is_tiled_over_atoms(S, monkeypatch):
@@ -648,6 +670,54 @@ def test_argmin_numpy_rules(S):
     assert_array_equal(amin.cpu().numpy(), np.amin(full, axis=-1))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind_name", ["normalized", "simple", "kernel2"])
+def test_row_minima_fused_into_the_tensor_core_epilogue(S, dtype, kind_name):
+    """soap_pairs(path=TENSOR, out=NULL, argmin_out, min_out): the minima kept by the tcgen05 epilogue equal
+    numpy.argmin / numpy.amin of the matrix the same path writes -- ties, NaNs, ragged tile edges included --
+    and soap_pairs_rowmin's exclude_offset drops the self distance of a row block."""
+    import torch
+    from cpctools_b200.classify import pairs_device
+    from cpctools_b200 import _lib
+
+    fn, okind, power = _kinds(S)[kind_name]
+    kind = {"normalized": _lib.KIND_NORMALIZED, "simple": _lib.KIND_SIMPLE, "kernel2": _lib.KIND_KERNEL}[kind_name]
+    rng = np.random.default_rng(11)
+    Y = O.normalizeArray(rng.random((3001, 576))).astype(dtype)
+    Y[1500] = Y[77]          # exact tie: the earlier column wins
+    Y[2999] = Y[78]
+    if kind_name != "normalized":
+        Y[2100] = 0.0        # zero vector -> NaN under the cosine kinds: the first NaN wins
+    X = Y[640 : 640 + 777].copy()
+    Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda()
+    full = pairs_device(Xd, Yd, kind, power, path=_lib.PAIRS_TENSOR).cpu().numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        amin, arg = pairs_device(Xd, Yd, kind, power, want_argmin=True)
+        assert_array_equal(arg.cpu().numpy(), np.argmin(full, axis=-1))
+        assert_array_equal(amin.cpu().numpy(), np.amin(full, axis=-1).astype(np.float64))
+        if kind_name == "simple":  # (the unclipped kernel may already give NaN on a row's own column)
+            assert (arg.cpu().numpy() == 2100).all() and np.isnan(amin.cpu().numpy()).all()
+        # the matrix AND the minima in one call
+        out = torch.empty((777, 3001), dtype=Xd.dtype, device="cuda")
+        amin2, arg2 = pairs_device(Xd, Yd, kind, power, out=out, want_argmin=True)
+        assert_array_equal(out.cpu().numpy(), full)
+        assert_array_equal(arg2.cpu().numpy(), arg.cpu().numpy())
+        # nearest OTHER vector: row i of the block is vector 640 + i
+        if kind_name == "normalized":
+            amin3, arg3 = pairs_device(Xd, Yd, kind, power, want_argmin=True, exclude_offset=640)
+            masked = full.astype(np.float64).copy()
+            masked[np.arange(777), 640 + np.arange(777)] = np.inf
+            assert_array_equal(arg3.cpu().numpy(), np.argmin(masked, axis=-1))
+            assert_array_equal(amin3.cpu().numpy(), np.amin(masked, axis=-1))
+    # against the oracle by the parity rule (independent of the matrix path)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = O.getDistanceBetween_batched(X.astype(np.float64), Y.astype(np.float64), okind, power)
+    if kind_name == "normalized":
+        assert_distance_parity(amin.cpu().numpy(), np.amin(want, axis=-1), "f64" if dtype == np.float64 else "f32")
+
+
 # ------------------------------------------------------------------ size-independent properties at scale
 def test_properties_at_benchmark_row_sizes(S):
     """Config-2/3 vectors (2 species, Dc 1224 -> Df 1728) on device-generated data too large for the
@@ -902,7 +972,12 @@ def test_fuzz_random_shapes_against_oracle(S):
         want_full = O.fillSOAPVectorFromdscribe(raw, lmax, nmax, **kw)
         assert_array_equal(S.fillSOAPVectorFromdscribe(raw, lmax, nmax, **kw), want_full)
         Xn = O.normalizeArray(want_full.astype(np.float64))
-        assert_allclose(S.fillAndNormalize(raw, lmax, nmax, **kw), O.normalizeArray(want_full), rtol=1e-12 if dtype == np.float64 else 1e-6, atol=0)
+        fn = S.fillAndNormalize(raw, lmax, nmax, **kw)
+        assert fn.dtype == dtype
+        # 1e-12 / 1e-6 against the exactly normalised vectors; float32 data additionally against the reference's OWN
+        # float32 arithmetic, which carries two more fp32 roundings (norm and quotient): 2e-6
+        assert_allclose(fn, Xn, rtol=1e-12 if dtype == np.float64 else 1e-6, atol=0)
+        assert_allclose(fn, O.normalizeArray(want_full), rtol=1e-12 if dtype == np.float64 else 2e-6, atol=0)
         nw = int(rng.integers(1, 5))
         windows = sorted(set(int(w) for w in rng.integers(1, F, size=nw)))
         got = S.timeSOAPfromCompressed(raw, lmax, nmax, windows=windows, returnDiff=False, **kw)
