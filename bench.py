@@ -379,13 +379,31 @@ def run_gpu_arm(args):
         nbytes = sum(int(f.numel()) * 8 for f in full)
         gather = {"collective": "NCCL all_gather_into_tensor of the t[F-w, A/G] slabs + one interleaving pass (every rank ends with t[F-w, A])",
                   "bytes_per_rank_out": nbytes, "ms": gms, "GBps_per_rank": nbytes / gms / 1e6}
-        # (b) overlapped: K steps, each step's slabs gathered on a side stream while the next step computes
+        # (b) overlapped: K steps, each step's slabs gathered on a side stream while the next step computes.
+        # The sweep is a persistent kernel that owns every SM's shared memory, so a NCCL kernel cannot run beside
+        # it; the gather is done by the COPY ENGINES instead (sharding.PeerGather: symmetric memory, one strided
+        # cudaMemcpy2DAsync per slab and peer straight into the [F-w, A] layout).  Fallback if symmetric memory is
+        # unavailable: NCCL on the side stream with a few SMs left free by the sweep (soap_reserve_sms).
         side = torch.cuda.Stream()
-        barrier()
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o0.record()
+        peer = None
+        try:
+            from cpctools_b200.sharding import PeerGather
+
+            if total_atoms % world:
+                raise RuntimeError("unequal shards")
+            peer = PeerGather([frames - w for w in WINDOWS], atoms)
+            method = "copy engines over NVLink into symmetric memory (sharding.PeerGather), no SM used"
+        except Exception as exc:  # noqa: BLE001
+            method = f"NCCL on a side stream, {args.reserve_sms} SMs reserved (symmetric memory unavailable: {str(exc)[:80]})"
+            _lib.check(lib.soap_reserve_sms(args.reserve_sms), "soap_reserve_sms")
         keep = None
-        for k in range(args.steps):
+        last = 0
+        for k in range(2 + args.steps):  # two untimed rounds first (allocator pools, communicators, mappings)
+            if k == 2:
+                torch.cuda.current_stream().wait_stream(side)
+                barrier()
+                o0.record()
             ts_k, dts_k = step()
             done = torch.cuda.Event()
             done.record()
@@ -393,15 +411,34 @@ def run_gpu_arm(args):
                 side.wait_event(done)
                 for t in ts_k:
                     t.record_stream(side)
-                keep = [gather_columns(t, total_atoms) for t in ts_k]
+                if peer is not None:
+                    last = peer.push(ts_k)
+                else:
+                    keep = [gather_columns(t, total_atoms) for t in ts_k]
         torch.cuda.current_stream().wait_stream(side)
         o1.record()
         barrier()
+        if peer is None:
+            _lib.check(lib.soap_reserve_sms(0), "soap_reserve_sms")
         oms = _allreduce(dist, world, torch, o0.elapsed_time(o1), dist.ReduceOp.MAX)
+        gather["overlapped_method"] = method
         gather["overlapped_ms_per_step"] = oms / args.steps
         gather["value_with_gather"] = pairs_step * args.steps / (oms * 1e-3)
         gather["efficiency_vs_no_gather"] = (elapsed_ms / args.steps) / (oms / args.steps)
-        full = keep
+        if peer is not None:
+            # alone, for the bandwidth figure
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            last = peer.push(ts_k)
+            p1.record()
+            peer.finish()
+            pms = _allreduce(dist, world, torch, p0.elapsed_time(p1), dist.ReduceOp.MAX)
+            gather["peer_gather_alone_ms"] = pms
+            gather["peer_gather_GBps_per_rank"] = nbytes / pms / 1e6
+            full = [v.clone() for v in peer.views(last)]
+        else:
+            full = keep
         del keep
 
         # ---- correctness of what ran under NCCL: (1) every rank recomputes the first atoms of its RIGHT
@@ -659,7 +696,7 @@ def run_quippy(args, torch, dist, _lib, S, rank, world, peak):
         res[name] = t
         out[name] = {"kernel_ms": kms, "ms_per_call": ms, "GBps": nbytes / kms / 1e6, "frac": nbytes / kms / 1e6 / peak,
                      "pairs_per_s_total": (frames - 1) * atoms * world / (ms * 1e-3),
-                     "note": None if (dq * es) % 16 == 0 else "rows are not 16-byte multiples: padded once on the device before the kernel (inside ms_per_call, outside kernel_ms)"}
+                     "note": None if (dq * es) % 16 == 0 else "rows of 8 mod 16 bytes: fetched by TMA through 16-byte aligned windows, the foreign elements of the first / last unit masked"}
     d2 = float((res["f32"] ** 2 - res["f64"] ** 2).abs().max().item())
     big = res["f64"] >= 0.25
     rel = float(((res["f32"] - res["f64"]).abs() / res["f64"])[big].max().item()) if bool(big.any()) else 0.0
@@ -801,7 +838,26 @@ def run_allpairs(args, torch, dist, _lib, rank, world, tensor_peaks=None):
             "checksum_sample": float(chk.item()),
         }
         out["rows_per_gpu"] = rows.stop - rows.start
-        del block
+        # per-row nearest OTHER vector (min / argmin over the whole row of the 200 000-column matrix) fused into the
+        # tcgen05 epilogue: nothing of the block is written ("gather only ... per-row min/argmin")
+        rm = lambda: pairs_device(X[rows], X, _lib.KIND_NORMALIZED, 1, want_argmin=True, exclude_offset=rows.start)
+        amin, arg = rm()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            amin, arg = rm()
+        e1.record()
+        torch.cuda.synchronize()
+        rm_ms = _allreduce(dist, world, torch, e0.elapsed_time(e1) / reps, dist.ReduceOp.MAX if world > 1 else None)
+        sub = block[:256].double().clone()
+        sub[torch.arange(256, device="cuda"), rows.start + torch.arange(256, device="cuda")] = float("inf")
+        smin, sarg = sub.min(dim=1)
+        rm_ok = bool(torch.equal(smin, amin[:256]) and torch.equal(sarg.to(torch.int32), arg[:256]))
+        parity_ok = parity_ok and rm_ok
+        out[name]["row_minima"] = {"ms_per_step": rm_ms, "pairs_per_s": pairs / (rm_ms * 1e-3), "matrix_written": False,
+                                   "matches_matrix_rows_0_255": rm_ok,
+                                   "api": "soap_pairs_rowmin(out=NULL, exclude_offset=first row of the block)"}
+        del block, sub
         torch.cuda.empty_cache()
         # the public all-pairs call getDistanceBetween(S, S, f) on one GPU: data is spectra, so only the
         # upper-triangular tiles are computed and mirrored (n_sym^2 ordered pairs delivered)
@@ -849,6 +905,7 @@ def main():
     ap.add_argument("--cpu-atoms", type=int, default=150, help="atoms of the cpu_baseline sample inside the GPU arm (~10 s)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-allpairs", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=8, help="SMs the sweep leaves to the overlapped NCCL gather (N > 1)")
     ap.add_argument("--no-extra", action="store_true", help="skip the expand (configs[1]) and quippy (configs[4]) objects")
     ap.add_argument("--expand-frames", type=int, default=100)
     ap.add_argument("--expand-atoms", type=int, default=10000)

@@ -95,6 +95,47 @@ class _HostStager:
         return dev
 
 
+    def upload_rows(self, arr: np.ndarray, lo: int, hi: int):
+        """Frames ``f`` of ``arr[f, lo:hi, :]`` (each a contiguous run of the host array) -> one flat device buffer."""
+        th = torch
+        F, A, D = arr.shape
+        row = (hi - lo) * D * arr.dtype.itemsize
+        n = F * row
+        src = arr.reshape(F, A * D).view(np.uint8)[:, lo * D * arr.dtype.itemsize : hi * D * arr.dtype.itemsize]
+        per = max(1, self.CHUNK // max(1, row))  # frames per pinned chunk
+        with self.lock:
+            if self.stream is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self.stream = th.cuda.Stream()
+                self.pool = ThreadPoolExecutor(self.threads)
+            main = th.cuda.current_stream()
+            dev = th.empty(n, dtype=th.uint8, device="cuda")
+            self.stream.wait_stream(main)
+            k = 0
+            for f0 in range(0, F, per):
+                f1 = min(F, f0 + per)
+                m = (f1 - f0) * row
+                need = max(self.CHUNK, m)
+                if self.bufs[k] is None or self.bufs[k].numel() < need:
+                    if self.events[k] is not None:
+                        self.events[k].synchronize()
+                    self.bufs[k] = th.empty(need, dtype=th.uint8, pin_memory=True)
+                if self.events[k] is not None:
+                    self.events[k].synchronize()
+                dst = self.bufs[k].numpy()[:m].reshape(f1 - f0, row)
+                cuts = [f0 + (f1 - f0) * i // self.threads for i in range(self.threads + 1)]
+                list(self.pool.map(lambda ab: np.copyto(dst[ab[0] - f0 : ab[1] - f0], src[ab[0] : ab[1]]), zip(cuts[:-1], cuts[1:])))
+                with th.cuda.stream(self.stream):
+                    dev[f0 * row : f0 * row + m].copy_(self.bufs[k][:m], non_blocking=True)
+                    ev = th.cuda.Event()
+                    ev.record(self.stream)
+                self.events[k] = ev
+                k ^= 1
+            main.wait_stream(self.stream)
+            dev.record_stream(self.stream)
+        return dev
+
     def download(self, t) -> np.ndarray:
         """HBM -> fresh pageable numpy array, the mirror image of :meth:`upload` (a plain ``.cpu()`` into
         untouched pageable memory runs at a fraction of the link rate: one thread takes all the page faults)."""
@@ -144,14 +185,38 @@ class _HostStager:
         return out
 
 
-_stager = None
+_stagers = {}
+_stagers_lock = None
+
+
+def _get_stager() -> "_HostStager":
+    """One stager (two pinned buffers + a copy stream) per device: several devices are fed from several host
+    threads at once (``analysis`` fans a host trajectory out over all visible GPUs)."""
+    global _stagers_lock
+    import threading
+
+    if _stagers_lock is None:
+        _stagers_lock = threading.Lock()
+    dev = torch.cuda.current_device()
+    with _stagers_lock:
+        st = _stagers.get(dev)
+        if st is None:
+            st = _stagers[dev] = _HostStager()
+        return st
 
 
 def _staged_upload(arr: np.ndarray, tdtype):
-    global _stager
-    if _stager is None:
-        _stager = _HostStager()
-    return _stager.upload(arr).view(tdtype).view(*arr.shape)
+    return _get_stager().upload(arr).view(tdtype).view(*arr.shape)
+
+
+def upload_atom_range(arr: np.ndarray, lo: int, hi: int):
+    """``arr[:, lo:hi, :]`` of a C-contiguous host array ``[F, A, D]`` -> contiguous CUDA tensor ``[F, hi-lo, D]``
+    through the pinned buffers (the strided rows are gathered by the stager's host threads; numpy's own
+    ``ascontiguousarray`` would do it on one thread at a few GB/s)."""
+    th = require_cuda()
+    F, A, D = arr.shape
+    tdtype = th.from_numpy(np.empty(0, dtype=arr.dtype)).dtype
+    return _get_stager().upload_rows(arr, lo, hi).view(tdtype).view(F, hi - lo, D)
 
 
 def to_device(x, dtype=None):
@@ -189,13 +254,42 @@ def to_device(x, dtype=None):
 
 
 def to_host(t) -> np.ndarray:
-    global _stager
     if t.is_cuda and t.numel() * t.element_size() >= _HostStager.MIN_BYTES and t.dtype in (
             torch.float32, torch.float64, torch.int32, torch.int64):
-        if _stager is None:
-            _stager = _HostStager()
-        return _stager.download(t)
+        with torch.cuda.device(t.device):
+            return _get_stager().download(t)
     return t.detach().cpu().numpy()
+
+
+def resolve_devices(devices=None, nbytes: int = 0):
+    """Device indices a HOST input is fanned out over.  ``devices``: ``None`` (policy below), ``"all"``, an int
+    or a sequence of ints.  Policy for ``None``: the environment variable ``SOAP_B200_DEVICES`` (``all`` or a comma
+    separated list) if set; the current device alone inside a ``torch.distributed`` job (one process per GPU
+    already) or for small inputs; otherwise every visible GPU."""
+    import os
+
+    th = require_cuda()
+    cur = th.cuda.current_device()
+    if devices is None:
+        env = os.environ.get("SOAP_B200_DEVICES", "").strip()
+        if env:
+            devices = env
+        elif int(os.environ.get("WORLD_SIZE", "1")) > 1 or (th.distributed.is_available() and th.distributed.is_initialized()):
+            return [cur]
+        elif nbytes < (1 << 30):
+            return [cur]
+        else:
+            devices = "all"
+    if isinstance(devices, str):
+        if devices.lower() == "all":
+            return list(range(th.cuda.device_count()))
+        devices = [int(d) for d in devices.split(",") if d.strip()]
+    if isinstance(devices, int):
+        devices = [devices]
+    devices = [int(d) for d in devices]
+    if not devices or any(d < 0 or d >= th.cuda.device_count() for d in devices):
+        raise ValueError(f"devices={devices}: this process sees {th.cuda.device_count()} CUDA device(s)")
+    return devices
 
 
 def like_input(result, original):

@@ -34,6 +34,7 @@ SIGNATURES = {
     "soap_abi_version": (c_int, []),
     "soap_last_error": (c_char_p, []),
     "soap_launch_count": (c_int64, []),
+    "soap_reserve_sms": (c_int, [c_int]),
     "soap_profile_enable": (c_int, [c_int]),
     "soap_profile_read": (c_int, [c_int, POINTER(ctypes.c_float), c_int]),
     "soap_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),

@@ -114,41 +114,95 @@ def _atom_tiles(x, bytes_per_atom: int):
 
 
 def _run_windows(X, windows, kind, power, mult, simple):
-    """One device tile: the time-lag kernel, or (``simple``) the row stitching of ``timeSOAPsimple``."""
+    """One device tile: the time-lag kernel, or (``simple``) the row stitching of ``timeSOAPsimple``.
+    ``mult`` may be a callable returning the multiplicities ON THE CURRENT DEVICE."""
     if simple:
         return [_simple_rows(X, windows[0])]
-    return timelag_device(X, windows, kind, power, mult=mult)
+    return timelag_device(X, windows, kind, power, mult=mult() if callable(mult) else mult)
 
 
-def _tiled(x, windows, kind, power, mult, returnDiff, simple: bool = False):
+def _join_atoms(parts_per_window, like, returnDiff):
+    """Concatenate per-tile results along the atom axis (``t``: axis 1, ``dt``: axis 0)."""
+    th = _device.torch
+    res = []
+    for parts in parts_per_window:
+        cat_t = (lambda xs, d: th.cat(xs, dim=d)) if _device.is_tensor(like) else (lambda xs, d: np.concatenate(xs, axis=d))
+        if returnDiff:
+            res.append((cat_t([p[0] for p in parts], 1), cat_t([p[1] for p in parts], 0)))
+        else:
+            res.append(cat_t(parts, 1))
+    return res
+
+
+def _host_tile(x, lo, hi):
+    """Atoms ``lo:hi`` of a host trajectory as a contiguous CUDA tensor (strided rows gathered by host threads)."""
+    if (isinstance(x, np.ndarray) and x.ndim == 3 and x.flags.c_contiguous and x.dtype in (np.float32, np.float64)
+            and x.dtype.byteorder in "=|<" and (hi - lo) * x.shape[0] * x.shape[2] * x.itemsize >= _device._HostStager.MIN_BYTES):
+        return _device.upload_atom_range(x, lo, hi)
+    return _device.as_float_tensor(x[:, lo:hi, :])
+
+
+def _tiled(x, windows, kind, power, mult, returnDiff, simple: bool = False, devices=None, atoms=None):
     """Run the time-lag kernel over atom tiles of ``x``; returns per window ``t`` (and ``dt``) in the
-    container type of ``x``.  ``simple``: ``windows == [w]`` and the rows are those of ``timeSOAPsimple``."""
+    container type of ``x``.  ``simple``: ``windows == [w]`` and the rows are those of ``timeSOAPsimple``.
+
+    HOST inputs are fanned out over ``devices`` (see :func:`_device.resolve_devices`: by default every visible
+    GPU for inputs of a GB or more outside ``torch.distributed`` jobs): contiguous atom ranges, one host thread
+    and one upload stream per device, so that a notebook call uses every PCIe link of the box.  ``atoms`` restricts
+    the work to an atom range of ``x`` (what a device worker is handed)."""
     th = _device.require_cuda()
-    F, D = int(x.shape[0]), int(x.shape[2])
+    F, A_all, D = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
     itemsize = 4 if str(getattr(x, "dtype", "")).endswith("float32") else 8
+    on_host = not (_device.is_tensor(x) and x.is_cuda)
+    lo0, hi0 = atoms if atoms is not None else (0, A_all)
+    if on_host and atoms is None:
+        devs = _device.resolve_devices(devices, F * A_all * D * itemsize)
+        if len(devs) > 1 and A_all >= len(devs):
+            return _fan_out(x, windows, kind, power, mult, returnDiff, simple, devs)
+        if devs[0] != th.cuda.current_device():
+            with th.cuda.device(devs[0]):
+                return _tiled(x, windows, kind, power, mult, returnDiff, simple, devices=devs, atoms=(0, A_all))
     per_atom = F * D * itemsize + F * 8 * (len(windows) + 1) * 8
-    if _pinned_host_tensor(x) and F * int(x.shape[1]) * D * itemsize >= PIPELINE_MIN_BYTES:
-        return _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom, simple)
-    tiles = _atom_tiles(x, per_atom)
-    if len(tiles) == 1:
+    if _pinned_host_tensor(x) and F * (hi0 - lo0) * D * itemsize >= PIPELINE_MIN_BYTES:
+        return _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom, simple, (lo0, hi0))
+    if not on_host:
+        return [_finish(t, x, returnDiff) for t in _run_windows(_device.as_float_tensor(x), windows, kind, power, mult, simple)]
+    tiles = [(lo0 + lo, lo0 + hi) for lo, hi in _atom_tiles(x[:, lo0:hi0], per_atom)]
+    if tiles == [(0, A_all)]:
         X = _device.as_float_tensor(x)
         return [_finish(t, x, returnDiff) for t in _run_windows(X, windows, kind, power, mult, simple)]
     outs = [[] for _ in windows]
     for lo, hi in tiles:
-        X = _device.as_float_tensor(x[:, lo:hi, :])
+        X = _host_tile(x, lo, hi)
         for k, t in enumerate(_run_windows(X, windows, kind, power, mult, simple)):
             outs[k].append(_finish(t, x, returnDiff))
         del X
-    res = []
-    for parts in outs:
-        if returnDiff:
-            if _device.is_tensor(x):
-                res.append((th.cat([p[0] for p in parts], dim=1), th.cat([p[1] for p in parts], dim=0)))
-            else:
-                res.append((np.concatenate([p[0] for p in parts], axis=1), np.concatenate([p[1] for p in parts], axis=0)))
-        else:
-            res.append(th.cat(parts, dim=1) if _device.is_tensor(x) else np.concatenate(parts, axis=1))
-    return res
+    return _join_atoms(outs, x, returnDiff)
+
+
+def _fan_out(x, windows, kind, power, mult, returnDiff, simple, devs):
+    """One host thread per device, each taking a contiguous atom range of the host trajectory through the
+    single-device path (its own pinned staging buffers, copy stream and kernels); results joined on the host."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from .sharding import shard_range
+
+    th = _device.require_cuda()
+    A = int(x.shape[1])
+    ranges = [shard_range(A, i, len(devs)) for i in range(len(devs))]
+
+    def work(i):
+        r = ranges[i]
+        if r.stop == r.start:
+            return None
+        with th.cuda.device(devs[i]):
+            res = _tiled(x, windows, kind, power, mult, returnDiff, simple, devices=[devs[i]], atoms=(r.start, r.stop))
+            th.cuda.synchronize()
+        return res
+
+    with ThreadPoolExecutor(len(devs)) as pool:
+        parts = [p for p in pool.map(work, range(len(devs))) if p is not None]
+    return _join_atoms([[p[k] for p in parts] for k in range(len(windows))], x, returnDiff)
 
 
 #: pinned host trajectories at least this large are uploaded in atom tiles while the previous tile computes
@@ -162,14 +216,16 @@ def _pinned_host_tensor(x) -> bool:
             and x.dtype in (_device.torch.float32, _device.torch.float64))
 
 
-def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom, simple: bool = False):
+def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom, simple: bool = False, atoms=None):
     """Pinned host trajectory -> host results with the link kept busy: atom tiles ``x[:, lo:hi, :]`` are
     uploaded on a copy stream (strided ``cudaMemcpy2DAsync`` into one of two device buffers) while the
     previous tile is processed.  The step then costs the H2D time of ``x`` plus the tail of the last tile and
     one staged download of the (small) results."""
     th = _device.require_cuda()
     lib = _lib.load()
-    F, A, D = (int(v) for v in x.shape)
+    F, A_all, D = (int(v) for v in x.shape)
+    a0, a1 = atoms if atoms is not None else (0, A_all)
+    A = a1 - a0  # the atoms this call works on (results are [F-w, A] / [A, F-w-1])
     es = x.element_size()
     free, _ = th.cuda.mem_get_info()
     n_tiles = max(2, -(-F * A * D * es // PIPELINE_TILE_BYTES))
@@ -198,7 +254,7 @@ def _tiled_pipelined(x, windows, kind, power, mult, returnDiff, per_atom, simple
             if i >= 2:
                 copy_stream.wait_event(done[i - 2])  # the tile that last used this buffer has been consumed
             rc = lib.soap_copy_rows(
-                bufs[i & 1].data_ptr(), (hi - lo) * D * es, x.data_ptr() + lo * D * es, A * D * es, (hi - lo) * D * es, F, 1,
+                bufs[i & 1].data_ptr(), (hi - lo) * D * es, x.data_ptr() + (a0 + lo) * D * es, A_all * D * es, (hi - lo) * D * es, F, 1,
                 int(copy_stream.cuda_stream),
             )
             _lib.check(rc, "soap_copy_rows")
@@ -237,8 +293,12 @@ def timeSOAP(
     backward: bool = False,
     returnDiff: bool = True,
     distanceFunction: callable = simpleSOAPdistance,
+    devices=None,
 ):
     """performs the 'timeSOAP' analysis on the given SOAP trajectory (analysis.py:13-69).
+
+    ``devices`` (extension, host inputs only): GPUs the atoms are fanned out over -- ``None`` = every visible GPU
+    for trajectories of a GB or more (one process, one upload stream per device), ``"all"``, an index or a list.
 
     ``t[f-window, a] = distanceFunction(X[f, a], X[f-window, a])``; returns ``t`` (float64,
     ``(frames-window, natoms)``) and, if ``returnDiff``, ``numpy.diff(t.T, axis=-1)``.  ``stride`` and
@@ -249,7 +309,7 @@ def timeSOAP(
     kind, power = resolve_distance(distanceFunction)
     if len(SOAPTrajectory.shape) != 3:
         raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
-    return _tiled(SOAPTrajectory, [int(window)], kind, power, None, returnDiff)[0]
+    return _tiled(SOAPTrajectory, [int(window)], kind, power, None, returnDiff, devices=devices)[0]
 
 
 def tempoSOAP(*args, **kwargs):
@@ -257,7 +317,8 @@ def tempoSOAP(*args, **kwargs):
     return timeSOAP(*args, **kwargs)
 
 
-def timeSOAPsweep(SOAPTrajectory, windows=(1, 5, 10, 50), returnDiff: bool = True, distanceFunction: callable = simpleSOAPdistance):
+def timeSOAPsweep(SOAPTrajectory, windows=(1, 5, 10, 50), returnDiff: bool = True, distanceFunction: callable = simpleSOAPdistance,
+                  devices=None):
     """``[timeSOAP(X, window=w, ...) for w in windows]`` with ONE pass over ``X`` per group of four
     windows (no reference counterpart: the reference would be called once per window)."""
     n_frames = int(SOAPTrajectory.shape[0])
@@ -266,7 +327,7 @@ def timeSOAPsweep(SOAPTrajectory, windows=(1, 5, 10, 50), returnDiff: bool = Tru
     kind, power = resolve_distance(distanceFunction)
     if len(SOAPTrajectory.shape) != 3:
         raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
-    return _tiled(SOAPTrajectory, [int(w) for w in windows], kind, power, None, returnDiff)
+    return _tiled(SOAPTrajectory, [int(w) for w in windows], kind, power, None, returnDiff, devices=devices)
 
 
 def timeSOAPfromCompressed(
@@ -279,6 +340,7 @@ def timeSOAPfromCompressed(
     returnDiff: bool = True,
     distanceFunction: callable = simpleSOAPdistance,
     quippy: bool = False,
+    devices=None,
 ):
     """``timeSOAP(normalizeArray(fillSOAPVectorFromdscribe(x, ...)), window=w)`` for every ``w`` in
     ``windows`` WITHOUT materialising the expanded vectors: the dot products of the expanded
@@ -304,8 +366,10 @@ def timeSOAPfromCompressed(
         raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
     th = _device.require_cuda()
     f32 = str(soapFromdscribe.dtype).endswith("float32")
-    mult = plan.multiplicity_device(th.float32 if f32 else th.float64)
-    return _tiled(soapFromdscribe, [int(w) for w in windows], kind, power, mult, returnDiff)
+    tdtype = th.float32 if f32 else th.float64
+    # evaluated where the tile runs: a host trajectory may be fanned out over several devices
+    return _tiled(soapFromdscribe, [int(w) for w in windows], kind, power, lambda: plan.multiplicity_device(tdtype), returnDiff,
+                  devices=devices)
 
 
 def _simple_rows(X, window: int):
@@ -323,7 +387,8 @@ def _simple_rows(X, window: int):
     return t
 
 
-def timeSOAPsimple(SOAPTrajectory, window: int = 1, stride: int = None, backward: bool = False, returnDiff: bool = True):
+def timeSOAPsimple(SOAPTrajectory, window: int = 1, stride: int = None, backward: bool = False, returnDiff: bool = True,
+                   devices=None):
     """performs the 'timeSOAP' analysis on the given **normalized** SOAP trajectory (analysis.py:72-142).
 
     Euclidean distance between consecutive frames' versors.  Kept literally, including the
@@ -335,7 +400,7 @@ def timeSOAPsimple(SOAPTrajectory, window: int = 1, stride: int = None, backward
         raise ValueError("a SOAP trajectory must have shape (nFrames, nAtoms, SOAPlength)")
     # atoms are independent for the Euclidean kind too: host trajectories larger than HBM go through the same
     # atom tiles (and the pinned upload pipeline) as timeSOAP, the rows are stitched per tile
-    return _tiled(SOAPTrajectory, [int(window)], _lib.KIND_EUCLID, 1, None, returnDiff, simple=True)[0]
+    return _tiled(SOAPTrajectory, [int(window)], _lib.KIND_EUCLID, 1, None, returnDiff, simple=True, devices=devices)[0]
 
 
 def getTimeSOAPSimple(soapDataset, window: int = 1, stride: int = None, backward: bool = False):

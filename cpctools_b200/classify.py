@@ -149,14 +149,49 @@ def pairs_device(data, spectra, kind: int, power: int = 1, path: int = _lib.PAIR
     return out
 
 
-def getDistanceBetween(data, spectra, distanceCalculator: Callable):
+def _pairs_fan_out(data, spectra, kind, power, devs):
+    """Host arrays: row blocks of ``data`` over the devices (the vector set ``spectra`` replicated), one host
+    thread per device, the blocks written into one host matrix."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from .sharding import shard_range
+
+    th = _device.require_cuda()
+    a = np.ascontiguousarray(np.asarray(data))
+    b = np.ascontiguousarray(np.asarray(spectra, dtype=a.dtype))
+    a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    out = np.empty((a2.shape[0], b2.shape[0]), dtype=a.dtype if a.dtype in (np.float32, np.float64) else np.float64)
+
+    def work(i):
+        rows = shard_range(a2.shape[0], i, len(devs))
+        if rows.stop == rows.start:
+            return
+        with th.cuda.device(devs[i]):
+            da, db = _device.as_float_tensor(a2[rows]), _device.as_float_tensor(b2)
+            out[rows] = _device.to_host(pairs_device(da, db.to(da.dtype), kind, power))
+
+    with ThreadPoolExecutor(len(devs)) as pool:
+        list(pool.map(work, range(len(devs))))
+    return out
+
+
+def getDistanceBetween(data, spectra, distanceCalculator: Callable, devices=None):
     """Array of the distances between ``data`` and ``spectra`` (classify.py:96-117).
 
     ``out[i, j] = distanceCalculator(data[i], spectra[j])``, shape ``(len(data), len(spectra))``,
     dtype ``data.dtype``.  ``getDistanceBetween(X, X, f)`` is the all-pairs SOAP distance matrix
-    (tensor-core GEMM with the distance as its epilogue when the matrix is large)."""
+    (tensor-core GEMM with the distance as its epilogue when the matrix is large).  ``devices`` (extension, host
+    arrays only): row blocks are fanned out over these GPUs, by default over every visible one when the matrix
+    has 1e9 entries or more."""
     kind, power = resolve_distance(distanceCalculator)
     th = _device.require_cuda()
+    if not _device.is_tensor(data) and not _device.is_tensor(spectra):
+        entries = int(np.shape(data)[0]) * int(np.shape(spectra)[0])
+        devs = _device.resolve_devices(devices, (1 << 30) if entries >= 10 ** 9 else 0)
+        if len(devs) > 1 and int(np.shape(data)[0]) >= 128 * len(devs):
+            res = _pairs_fan_out(data, spectra, kind, power, devs)
+            want = np.asarray(data).dtype
+            return res if res.dtype == want else res.astype(want)
     a = _device.as_float_tensor(data)
     b = _device.as_float_tensor(spectra)
     if a.dtype != b.dtype:

@@ -39,6 +39,12 @@ static int query_attr(cudaDeviceAttr attr, int dflt) {
   return val;
 }
 int num_sms() { return query_attr(cudaDevAttrMultiProcessorCount, 148); }
+static std::atomic<int> g_reserved_sms{0};
+// SMs the persistent kernels leave free (a collective or a copy kernel running beside them needs somewhere to go)
+int persistent_sms() {
+  const int n = num_sms() - g_reserved_sms.load(std::memory_order_relaxed);
+  return n < 1 ? 1 : n;
+}
 int max_smem_optin() { return query_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, 232448); }
 
 // ---- profiling hook ------------------------------------------------------------------------
@@ -129,6 +135,12 @@ extern "C" int soap_abi_version(void) { return SOAP_B200_ABI_VERSION; }
 extern "C" const char *soap_last_error(void) { return last_error().c_str(); }
 extern "C" int64_t soap_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+extern "C" int soap_reserve_sms(int n) {
+  SOAP_REQUIRE(n >= 0, "soap_reserve_sms: negative count");
+  g_reserved_sms.store(n, std::memory_order_relaxed);
+  return SOAP_OK;
+}
+
 extern "C" int soap_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto *r : g_prof) {
@@ -172,14 +184,16 @@ extern "C" int soap_fill_uniform(void *out, int64_t n, uint64_t seed, int dtype,
 }
 
 // strided host <-> device row copy on a stream (cudaMemcpy2DAsync): the atom tiles of a pinned host
-// trajectory [F][A][D] are F rows of (tile atoms * D) elements with a pitch of A * D elements
+// trajectory [F][A][D] are F rows of (tile atoms * D) elements with a pitch of A * D elements.
+// to_device == 2: both ends on devices (a peer-mapped buffer included): the copy engines place a rank's result
+// slab [rows][A/G] straight into the [rows][A] array of another GPU, no SM involved
 extern "C" int soap_copy_rows(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
                               size_t rows, int to_device, void *stream) {
   if (row_bytes == 0 || rows == 0) return SOAP_OK;
   SOAP_REQUIRE(dst && src, "soap_copy_rows: null buffer");
   SOAP_REQUIRE(dst_pitch >= row_bytes && src_pitch >= row_bytes, "soap_copy_rows: pitch smaller than a row");
   SOAP_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows,
-                              to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                              to_device == 2 ? cudaMemcpyDefault : (to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost),
                               static_cast<cudaStream_t>(stream)));
   return SOAP_OK;
 }

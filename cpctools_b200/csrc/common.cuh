@@ -19,6 +19,7 @@ extern std::atomic<int64_t> g_launches;
 int set_error(int code, const char *fmt, ...);
 int check_launch(const char *what);
 int num_sms();
+int persistent_sms();  // num_sms() minus soap_reserve_sms()
 // profiling hook: RAII bracket of one kernel launch with CUDA events (no-op unless enabled)
 struct ProfScope {
   int id;

@@ -74,6 +74,68 @@ def gather_columns(local, n_total: int, group=None):
     return torch.cat(out, dim=-1)
 
 
+class PeerGather:
+    """All-gather of the ranks' ``t[F-w, A/G]`` slabs by the COPY ENGINES, straight into the ``[F-w, A]`` layout.
+
+    Every rank owns a symmetric-memory buffer (``torch.distributed._symmetric_memory``: CUDA VMM memory mapped
+    into all peers over NVLink) holding the full ``[rows, A]`` arrays of all windows; ``push`` issues, per slab and
+    peer, ONE strided ``cudaMemcpy2DAsync`` (``soap_copy_rows``) from the local slab into the column block of this
+    rank inside the peer's buffer.  No kernel runs: the gather overlaps the next sweep -- a persistent kernel that
+    owns every SM, beside which NCCL's copy kernel cannot start -- without taking SMs from it, and there is no
+    staging buffer or interleaving pass.  Equal shards only (``A % world == 0``); ``buffers`` of them rotate so
+    that a consumer may still read step k while step k+1 lands."""
+
+    def __init__(self, rows: Sequence[int], width: int, group=None, buffers: int = 2):
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self.rank, self.world = _world(group)
+        self.rows = [int(r) for r in rows]
+        self.width = int(width)
+        self.total_cols = self.width * self.world
+        self.group = group
+        self.lib = _lib
+        name = (group if group is not None else dist.group.WORLD).group_name
+        shape = (sum(self.rows), self.total_cols)
+        self.bufs = [symm.empty(shape, dtype=torch.float64, device="cuda") for _ in range(buffers)]
+        self.handles = [symm.rendezvous(b, name) for b in self.bufs]
+        self.peers = [[h.get_buffer(r, shape, torch.float64) for r in range(self.world)] for h in self.handles]
+        self.step = 0
+
+    def push(self, slabs):
+        """Queue the copies of this rank's slabs (one ``[rows_i, width]`` float64 CUDA tensor per window) on the
+        current stream; returns the index of the buffer they land in (on every rank)."""
+        b = self.step % len(self.bufs)
+        self.step += 1
+        stream = int(torch.cuda.current_stream().cuda_stream)
+        lib = self.lib.load()
+        pitch = self.total_cols * 8
+        off = 0
+        for slab, rows in zip(slabs, self.rows):
+            assert tuple(slab.shape) == (rows, self.width) and slab.dtype == torch.float64 and slab.is_contiguous()
+            for k in range(self.world):  # start with the neighbour: the links are loaded evenly
+                r = (self.rank + 1 + k) % self.world
+                dst = self.peers[b][r].data_ptr() + (off * self.total_cols + self.rank * self.width) * 8
+                self.lib.check(lib.soap_copy_rows(dst, pitch, slab.data_ptr(), self.width * 8, self.width * 8, rows, 2, stream),
+                               "soap_copy_rows")
+            off += rows
+        return b
+
+    def finish(self):
+        """Wait until the slabs of EVERY rank have landed here (local stream + a barrier over the group)."""
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=self.group)
+
+    def views(self, b: int):
+        """The gathered ``[rows_i, A]`` arrays of buffer ``b`` (valid after :meth:`finish`)."""
+        out, off = [], 0
+        for rows in self.rows:
+            out.append(self.bufs[b][off : off + rows])
+            off += rows
+        return out
+
+
 def gather_rows(local, n_total: int, group=None):
     """Same as :func:`gather_columns` for a partition of the FIRST axis."""
     rank, world = _world(group)

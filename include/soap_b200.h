@@ -175,7 +175,14 @@ int soap_residence_events(const int32_t *states, int64_t n_frames, int64_t n_ato
  * tiles x[:, lo:hi, :] of a pinned host trajectory while the previous tile is being processed.
  */
 int soap_copy_rows(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes, size_t rows,
-                   int to_device, void *stream);
+                   int to_device /* 1: host -> device, 0: device -> host, 2: device -> device (peer mapped included) */,
+                   void *stream);
+
+/* ---- SMs left free by the persistent kernels (soap_timelag runs one CTA per SM that owns the whole shared memory:
+ * a collective launched on another stream cannot start beside it).  soap_reserve_sms(n) makes them use n SMs fewer,
+ * so that e.g. the NCCL all-gather of the previous step's results overlaps the next sweep; 0 restores the default.
+ */
+int soap_reserve_sms(int n);
 
 /* ---- result gather: NCCL all-gathers the ranks' t[F-w][A/G] slabs into
  * buf[G][rows][width]; this turns them into the out[rows][G * width] array of the reference layout

@@ -413,6 +413,42 @@ def test_host_trajectory_larger_than_budget_is_tiled_over_atoms(S, monkeypatch):
     assert_distance_parity(res[1], O.timeSOAP_batched(X, window=2, returnDiff=False), "f64")
 
 
+def test_host_inputs_fan_out_over_devices(S, monkeypatch):
+    """``devices=``: a host trajectory / vector set is split into contiguous atom ranges / row blocks, one host
+    thread per device (here the same device twice: the code path, not the speed-up); results are those of the
+    single-device call -- numpy, pinned tensor (pipelined upload of a sub-range) and the distance matrix."""
+    import torch
+    from cpctools_b200 import analysis
+
+    attrs, dc = dscribe_attrs(8, 8, ["H", "O"])
+    kw = dict(atomTypes=["H", "O"], atomicSlices=_slices_from_attrs(attrs))
+    raw = synthetic_soap((60, 41, dc), seed=21, kind="W")
+    one = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1, 7), devices=[0], **kw)
+    two = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1, 7), devices=[0, 0], **kw)
+    for (t1, d1), (t2, d2) in zip(one, two):
+        assert isinstance(t2, np.ndarray) and t2.shape == t1.shape and d2.shape == d1.shape
+        assert_array_equal(t2, t1)
+        assert_array_equal(d2, d1)
+    monkeypatch.setattr(analysis, "PIPELINE_MIN_BYTES", 1)
+    pinned = torch.from_numpy(raw).pin_memory()
+    three = S.timeSOAPfromCompressed(pinned, 8, 8, windows=(1, 7), devices=[0, 0, 0], **kw)
+    for (t1, d1), (t3, d3) in zip(one, three):
+        assert not t3.is_cuda
+        assert_array_equal(t3.numpy(), t1)
+        assert_array_equal(d3.numpy(), d1)
+    X = O.normalizeArray(np.random.default_rng(2).random((60, 41, 64)))
+    assert_array_equal(S.timeSOAP(X, window=3, devices=[0, 0])[0], S.timeSOAP(X, window=3, devices=0)[0])
+    assert_array_equal(S.timeSOAPsimple(X, window=2, devices=[0, 0])[0], S.timeSOAPsimple(X, window=2)[0])
+    monkeypatch.setenv("SOAP_B200_DEVICES", "0,0")
+    assert_array_equal(S.timeSOAP(X, window=3)[0], S.timeSOAP(X, window=3, devices=0)[0])
+    monkeypatch.delenv("SOAP_B200_DEVICES")
+    with pytest.raises(ValueError, match="CUDA device"):
+        S.timeSOAP(X, window=3, devices=[0, 99])
+    V = O.normalizeArray(np.random.default_rng(3).random((700, 576)))
+    assert_array_equal(S.getDistanceBetween(V, V[:300], S.SOAPdistanceNormalized, devices=[0, 0]),
+                       S.getDistanceBetween(V, V[:300], S.SOAPdistanceNormalized, devices=[0]))
+
+
 def test_pinned_host_tensor_is_uploaded_in_overlapped_atom_tiles(S, monkeypatch):
     """a pinned host tensor takes the pipelined path (strided tile uploads on a copy stream, results
     downloaded per tile) and returns HOST tensors identical to the one-shot path."""
