@@ -317,7 +317,7 @@ def run_gpu_arm(args):
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_timelag_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_timelag_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read+write of one `ncu --set full` capture, scaled by the atom count
         tj = json.load(open(tpath))
         traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * atoms / tj["atoms"] * frames / 1000

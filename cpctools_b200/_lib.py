@@ -24,7 +24,7 @@ NVCC_FLAGS = (
 
 # dtype / kind / path codes of include/soap_b200.h
 F32, F64 = 0, 1
-KIND_SIMPLE, KIND_KERNEL, KIND_NORMALIZED, KIND_DOT, KIND_COSCLIP, KIND_EUCLID, KIND_NORMALIZED_FUSED = range(7)
+KIND_SIMPLE, KIND_KERNEL, KIND_NORMALIZED, KIND_DOT, KIND_COSCLIP, KIND_EUCLID, KIND_NORMALIZED_FUSED, KIND_EUCLID_NORMALIZED = range(8)
 PAIRS_AUTO, PAIRS_SIMT, PAIRS_TENSOR, PAIRS_TENSOR_NATIVE = 0, 1, 2, 3
 MAX_WINDOWS = 4
 NO_EXCLUDE = -(2 ** 63)  # SOAP_NO_EXCLUDE

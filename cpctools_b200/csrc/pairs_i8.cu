@@ -790,7 +790,13 @@ int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t 
   I8RowMin rm{argmin_out, min_out, excl};
   const I8RowMin *am = (argmin_out || min_out) ? &rm : nullptr;
   if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, 8, true, float);
-  if (kind == SOAP_KIND_NORMALIZED) return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, 8, false, float);
+  if (kind == SOAP_KIND_NORMALIZED) {
+    // SOAP_I8_TILE=80: two accumulator sets of N = 80 (the epilogue of a tile overlaps the MMAs of the next one; the
+    // N = 80 MMAs are shared-memory-operand bound) instead of one set of N = 160 (experiments, scripts/prof_block.py)
+    const char *tile = getenv("SOAP_I8_TILE");
+    if (tile && atoi(tile) == 80) return I8_LAUNCH(float, 3, 80, 64, 2, 4, true, 8, false, float);
+    return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, 8, false, float);
+  }
   return I8_LAUNCH(float, 3, 80, 128, 2, 2, false, 8, true, float);
 }
 

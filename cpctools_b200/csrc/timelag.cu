@@ -110,9 +110,10 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
 // U units (16 bytes each) of the lane's frame against the NW lagged frames.  All loads are issued
 // before the first use so that one warp keeps U*(NW+2) shared-memory requests in flight.
 // fp64: exact products accumulated by DFMA, separate chains for the two halves of a unit.
-template <int NW, int U, bool EUCLID, bool HM, bool CLEAN = false>
+template <int NW, int U, int EUCLID, bool HM, bool CLEAN = false>
 __device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
-                                                uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
+                                                uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)],
+                                                const double *sc = nullptr) {
   double2 m[U], x[U], y[NW][U];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
@@ -141,7 +142,9 @@ __device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr
 #pragma unroll
     for (int k = 0; k < NW; ++k) {
       if (EUCLID) {
-        const double d0 = x[j].x - y[k][j].x, d1 = x[j].y - y[k][j].y;
+        // EUCLID == 2: the rows are normalised on the fly, sc[0] = 1/|x|, sc[1 + k] = 1/|y_k| (zero norm -> 1)
+        const double d0 = EUCLID == 2 ? fma(x[j].x, sc[0], -(y[k][j].x * sc[1 + k])) : x[j].x - y[k][j].x;
+        const double d1 = EUCLID == 2 ? fma(x[j].y, sc[0], -(y[k][j].y * sc[1 + k])) : x[j].y - y[k][j].y;
         acc[2 * k + 2] = fma(m[j].x * d0, d0, acc[2 * k + 2]);
         acc[2 * k + 3] = fma(m[j].y * d1, d1, acc[2 * k + 3]);
       } else {
@@ -154,9 +157,10 @@ __device__ __forceinline__ void accum_units_f64(uint32_t m_addr, uint32_t x_addr
 
 // fp32 data: products and a chain of 4*U terms in fp32, chain sums promoted to double (one
 // conversion per 4*U products; the fp32 rounding is bounded to one short chain).
-template <int NW, int U, bool EUCLID, bool HM, bool CLEAN = false>
+template <int NW, int U, int EUCLID, bool HM, bool CLEAN = false>
 __device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
-                                                uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
+                                                uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)],
+                                                const double *sc = nullptr) {
   float4 m[U], x[U], y[NW][U];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
@@ -197,7 +201,16 @@ __device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       if (EUCLID) {
-        const float d0 = x[j].x - y[k][j].x, d1 = x[j].y - y[k][j].y, d2 = x[j].z - y[k][j].z, d3 = x[j].w - y[k][j].w;
+        float d0, d1, d2, d3;
+        if (EUCLID == 2) {  // normalised on the fly (float32 arithmetic, like the reference on float32 data)
+          const float sx = (float)sc[0], sy = (float)sc[1 + k];
+          d0 = fmaf(x[j].x, sx, -(y[k][j].x * sy));
+          d1 = fmaf(x[j].y, sx, -(y[k][j].y * sy));
+          d2 = fmaf(x[j].z, sx, -(y[k][j].z * sy));
+          d3 = fmaf(x[j].w, sx, -(y[k][j].w * sy));
+        } else {
+          d0 = x[j].x - y[k][j].x, d1 = x[j].y - y[k][j].y, d2 = x[j].z - y[k][j].z, d3 = x[j].w - y[k][j].w;
+        }
         s0 = fmaf(m[j].x * d0, d0, s0);
         s1 = fmaf(m[j].y * d1, d1, s1);
         s0 = fmaf(m[j].z * d2, d2, s0);
@@ -214,13 +227,14 @@ __device__ __forceinline__ void accum_units_f32(uint32_t m_addr, uint32_t x_addr
   }
 }
 
-template <typename T, int NW, int U, bool EUCLID, bool HM, bool CLEAN = false>
+template <typename T, int NW, int U, int EUCLID, bool HM, bool CLEAN = false>
 __device__ __forceinline__ void accum_units(uint32_t m_addr, uint32_t x_addr, const uint32_t (&y_addr)[NW],
-                                            uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)]) {
+                                            uint32_t off, uint32_t ustep, double (&acc)[2 * (NW + 1)],
+                                            const double *sc = nullptr) {
   if constexpr (sizeof(T) == 8)
-    accum_units_f64<NW, U, EUCLID, HM, CLEAN>(m_addr, x_addr, y_addr, off, ustep, acc);
+    accum_units_f64<NW, U, EUCLID, HM, CLEAN>(m_addr, x_addr, y_addr, off, ustep, acc, sc);
   else
-    accum_units_f32<NW, U, EUCLID, HM, CLEAN>(m_addr, x_addr, y_addr, off, ustep, acc);
+    accum_units_f32<NW, U, EUCLID, HM, CLEAN>(m_addr, x_addr, y_addr, off, ustep, acc, sc);
 }
 
 // Warp roles: warps 0..CW-1 consume (lane = frame), warp CW produces (TMA / cp.async), warp CW+1 reduces
@@ -286,10 +300,10 @@ __device__ __forceinline__ TlItem tl_item(int j, int split, int upp, int D, bool
   return it;
 }
 
-template <typename T, int NW, bool EUCLID, bool HAS_MULT, int CW, int UB>
+template <typename T, int NW, int EUCLID, bool HAS_MULT, int CW, int UB>
 __global__ void __launch_bounds__((CW + 2) * 32, 1)
     timelag_kernel(const T *__restrict__ X, const T *__restrict__ mult, double *__restrict__ sums,
-                   double *__restrict__ cta_acc,
+                   double *__restrict__ cta_acc, const double *__restrict__ inv_norm,
                    long long F, long long A, int D, int split, int upp, int stride, int R, int lag_blocks,
                    int mbuf, int4 win4, int bulk_ok, int mult_pitch, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -448,33 +462,41 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
         double acc[2 * Q];
 #pragma unroll
         for (int q = 0; q < 2 * Q; ++q) acc[q] = 0.0;
+        double sc[Q];  // EUCLID == 2: reciprocal norms of this lane's frame and of its lag partners
+        if constexpr (EUCLID == 2) {
+          const long long f = (long long)b * kBlk + lane;
+          const double *ia = inv_norm + (size_t)it.a * (size_t)F;
+          sc[0] = f < F ? ia[f] : 0.0;
+#pragma unroll
+          for (int q = 0; q < NW; ++q) sc[1 + q] = (f < F && f >= win[q]) ? ia[f - win[q]] : 0.0;
+        }
         mbar_wait(&full[s], (uint32_t)ph);
         int n = 0;
         // (masking the lanes past the last frame -- 24 of 32 in the last block at F = 1000 -- measured 3 % SLOWER:
         // the divergent loop costs more than the wavefronts it saves)
         if (head) {
-          accum_units<T, NW, 1, EUCLID, HAS_MULT, true>(m_addr, x_addr, y_addr, off0, ustep, acc);
+          accum_units<T, NW, 1, EUCLID, HAS_MULT, true>(m_addr, x_addr, y_addr, off0, ustep, acc, sc);
           n = 1;
         }
         if (bulk_ok & 4) n = my_units;  // diagnostic: no accumulation
         for (; n + UB <= my_units; n += UB)
-          accum_units<T, NW, UB, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+          accum_units<T, NW, UB, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc, sc);
         if constexpr (UB > 4) {
           if (n + 4 <= my_units) {
-            accum_units<T, NW, 4, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+            accum_units<T, NW, 4, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc, sc);
             n += 4;
           }
         }
         if constexpr (UB > 2) {
           if (n + 2 <= my_units) {
-            accum_units<T, NW, 2, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+            accum_units<T, NW, 2, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc, sc);
             n += 2;
           }
         }
         if (n < my_units)
-          accum_units<T, NW, 1, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc);
+          accum_units<T, NW, 1, EUCLID, HAS_MULT>(m_addr, x_addr, y_addr, off0 + n * ustep, ustep, acc, sc);
         if (tail && !(bulk_ok & 4))
-          accum_units<T, NW, 1, EUCLID, HAS_MULT, true>(m_addr, x_addr, y_addr, off0 + my_units * ustep, ustep, acc);
+          accum_units<T, NW, 1, EUCLID, HAS_MULT, true>(m_addr, x_addr, y_addr, off0 + my_units * ustep, ustep, acc, sc);
         // hand the partial sums to the reducer (it is ~10x faster than a block: this wait is free)
         if (g >= 1) mbar_wait(red_empty, (uint32_t)((g - 1) & 1));
         double *r = red + (size_t)warp * Q * 32;
@@ -587,7 +609,7 @@ static RbChoice rb_choose(int64_t F, int64_t A, int D, int es, const int *window
   RbChoice ch;
   memset(&ch, 0, sizeof(ch));
   const int mode = env_int("SOAP_TL_RB", -1);
-  if (mode != 1 || !bulk_ok || kind == SOAP_KIND_EUCLID || nw < 1 || nw > 4) return ch;
+  if (mode != 1 || !bulk_ok || kind == SOAP_KIND_EUCLID || kind == SOAP_KIND_EUCLID_NORMALIZED || nw < 1 || nw > 4) return ch;
   for (int k = 0; k < nw; ++k) ch.perm[k] = k;
   for (int i = 1; i < nw; ++i)
     for (int j = i; j > 0 && windows[ch.perm[j]] < windows[ch.perm[j - 1]]; --j) {
@@ -655,6 +677,42 @@ static int dispatch_timelag_rb(const void *X, const void *mult, double *scratch,
   return set_error(SOAP_EINVAL, "soap_timelag: no register-blocked variant for %d + %d windows", ch.ns, ch.nl);
 }
 
+// inv[a][f] = 1 / sqrt(sum_e m_e x[f][a][e]^2), 1 for a zero row (normalizeArray, utils.py:149-151): the norms of the
+// EXPANDED vectors from the compressed rows; one warp per row, 128-bit loads when the rows allow
+template <typename T>
+__global__ void __launch_bounds__(256)
+    row_inv_norm_kernel(const T *__restrict__ X, const T *__restrict__ mult, double *__restrict__ inv, long long F, long long A,
+                        int D, int vec_ok) {
+  constexpr int UE = 16 / (int)sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const long long nrows = F * A, nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += nwarps) {
+    const T *x = X + (size_t)r * D;
+    double acc = 0.0;
+    if (vec_ok) {
+      for (int u = lane; u < D / UE; u += 32) {
+        const int4 raw = ldg_stream16(x + u * UE);
+        const T *v = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+        for (int e = 0; e < UE; ++e) {
+          const double xv = (double)v[e], mv = mult ? (double)mult[u * UE + e] : 1.0;
+          acc = fma(xv * mv, xv, acc);
+        }
+      }
+    } else {
+      for (int e = lane; e < D; e += 32) {
+        const double xv = (double)x[e], mv = mult ? (double)mult[e] : 1.0;
+        acc = fma(xv * mv, xv, acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const long long f = r / A, a = r - f * A;
+      inv[(size_t)a * F + f] = acc == 0.0 ? 1.0 : 1.0 / sqrt(acc);
+    }
+  }
+}
+
 // shifted rows: table[ph][i] = multiplicity of element i - ph * lead of the row (ones when the caller passes none),
 // zero outside the row -- what masks the foreign elements of the first / last unit of an atom's window
 template <typename T>
@@ -667,15 +725,17 @@ __global__ void shift_mult_kernel(const T *__restrict__ mult, T *__restrict__ ou
 
 template <typename T, int NW, bool HM>
 static int launch_timelag(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D,
-                          const TimelagPlan &pl, const int *w, int kind, int bulk_ok, int mult_pitch, cudaStream_t s) {
+                          const TimelagPlan &pl, const int *w, int kind, int bulk_ok, int mult_pitch, const double *inv_norm,
+                          cudaStream_t s) {
   const int4 win4 = make_int4(w[0], NW > 1 ? w[1] : 0, NW > 2 ? w[2] : 0, NW > 3 ? w[3] : 0);
-  auto kern = (kind == SOAP_KIND_EUCLID) ? timelag_kernel<T, NW, true, HM, kTlWarps, 4>
-                                         : timelag_kernel<T, NW, false, HM, kTlWarps, 4>;
+  auto kern = (kind == SOAP_KIND_EUCLID) ? timelag_kernel<T, NW, 1, HM, kTlWarps, 4>
+              : (kind == SOAP_KIND_EUCLID_NORMALIZED) ? timelag_kernel<T, NW, 2, HM, kTlWarps, 4>
+                                                      : timelag_kernel<T, NW, 0, HM, kTlWarps, 4>;
   int cw = kTlWarps;
   if constexpr (NW == 4 && sizeof(T) == 8 && HM) {  // launch-shape experiments (scripts/tl_sweep.py)
-    if (kind != SOAP_KIND_EUCLID && pl.cw != kTlWarps) {
+    if (kind != SOAP_KIND_EUCLID && kind != SOAP_KIND_EUCLID_NORMALIZED && pl.cw != kTlWarps) {
       cw = pl.cw;
-#define TL_VAR(W, B) if (cw == W) kern = timelag_kernel<T, NW, false, HM, W, B>;
+#define TL_VAR(W, B) if (cw == W) kern = timelag_kernel<T, NW, 0, HM, W, B>;
       TL_VAR(4, 4) TL_VAR(6, 4) TL_VAR(10, 4) TL_VAR(12, 4)
 #undef TL_VAR
     }
@@ -715,7 +775,7 @@ static int launch_timelag(const void *X, const void *mult, double *scratch, int6
   }
   ProfScope prof(SOAP_PROF_TIMELAG, s);
   kern<<<(unsigned)grid, threads, pl.smem, s>>>(static_cast<const T *>(X), static_cast<const T *>(mult), scratch, cta_acc,
-                                                (long long)F, (long long)A, D, pl.split, pl.upp, pl.stride, pl.R,
+                                                inv_norm, (long long)F, (long long)A, D, pl.split, pl.upp, pl.stride, pl.R,
                                                 (pl.max_lag + kBlk - 1) / kBlk, pl.mbuf, win4, bulk_ok, mult_pitch, tmap);
   return check_launch("timelag_kernel");
 }
@@ -737,6 +797,8 @@ using namespace soapb;
 
 // room at the end of the scratch area for the zero-padded multiplicities (rows that are not whole units)
 static size_t tl_pad_bytes(int dim, int es) { return 2 * ((size_t)dim + 32) * es + 256; }
+// ... and, before it, for the reciprocal row norms of SOAP_KIND_EUCLID_NORMALIZED
+static size_t tl_inv_bytes(int64_t F, int64_t A) { return (size_t)F * A * sizeof(double) + 256; }
 
 static int check_windows(int64_t F, const int *w, int nw, const char *who) {
   SOAP_REQUIRE(w != nullptr && nw >= 1 && nw <= SOAP_MAX_WINDOWS, "%s: 1..%d windows per call", who, SOAP_MAX_WINDOWS);
@@ -762,13 +824,14 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
   }
   TimelagPlan pl;
   const int plan_dim = (((size_t)dim * es) % 16 != 0 && ((size_t)dim * es) % 8 == 0) ? dim + 8 / es : dim;  // shifted rows
-  if (!make_plan(n_frames, plan_dim, es, windows_host, n_windows, pl)) return rb_bytes + tl_pad_bytes(dim, es);
+  if (!make_plan(n_frames, plan_dim, es, windows_host, n_windows, pl))
+    return rb_bytes + tl_pad_bytes(dim, es) + tl_inv_bytes(n_frames, n_atoms);
   // totals sums[a][q][f] + one accumulator [q][frames padded to 32] per resident CTA
   const size_t padded = (size_t)((n_frames + kBlk - 1) / kBlk) * kBlk;
   size_t bytes = tl_atom_major(n_atoms)
                      ? ((size_t)n_atoms * pl.Q * (size_t)n_frames + (size_t)tl_max_grid() * pl.Q * padded) * sizeof(double)
                      : (size_t)n_atoms * pl.split * pl.Q * (size_t)n_frames * sizeof(double);
-  return (bytes > rb_bytes ? bytes : rb_bytes) + tl_pad_bytes(dim, es);
+  return (bytes > rb_bytes ? bytes : rb_bytes) + tl_pad_bytes(dim, es) + tl_inv_bytes(n_frames, n_atoms);
 }
 
 extern "C" int soap_timelag(const void *X, const void *mult, double *t, const int64_t *t_offsets_host,
@@ -777,7 +840,7 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
   SOAP_REQUIRE(n_frames > 0 && n_atoms > 0 && dim > 0, "soap_timelag: bad shape");
   SOAP_REQUIRE(X && t && t_offsets_host && scratch, "soap_timelag: null buffer");
   SOAP_REQUIRE(dtype == SOAP_F32 || dtype == SOAP_F64, "soap_timelag: dtype %d", dtype);
-  SOAP_REQUIRE(kind >= SOAP_KIND_SIMPLE && kind <= SOAP_KIND_NORMALIZED_FUSED, "soap_timelag: kind %d", kind);
+  SOAP_REQUIRE(kind >= SOAP_KIND_SIMPLE && kind <= SOAP_KIND_EUCLID_NORMALIZED, "soap_timelag: kind %d", kind);
   int rc = check_windows(n_frames, windows_host, n_windows, "soap_timelag");
   if (rc) return rc;
   const int es = dtype == SOAP_F64 ? 8 : 4;
@@ -788,6 +851,23 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
                 (((size_t)n_atoms * dim * es) % 16 == 0) && ((reinterpret_cast<uintptr_t>(mult) & 15) == 0);
   auto s = static_cast<cudaStream_t>(stream);
   auto sc = static_cast<double *>(scratch);
+  const size_t scratch_total = soap_timelag_scratch_bytes(n_frames, n_atoms, dim, dtype, windows_host, n_windows);
+  const double *inv_norm = nullptr;
+  if (kind == SOAP_KIND_EUCLID_NORMALIZED) {
+    // timeSOAPsimple on normalizeArray(fillSOAPVectorFromdscribe(x)) without materialising it: one pass for the
+    // norms of the expanded vectors (from the compressed rows and the multiplicities), then |x/|x| - y/|y||
+    double *inv = reinterpret_cast<double *>(
+        (reinterpret_cast<uintptr_t>(static_cast<char *>(scratch) + scratch_total - tl_pad_bytes(dim, es) - tl_inv_bytes(n_frames, n_atoms)) + 127) & ~(uintptr_t)127);
+    const int vec_ok = ((size_t)dim * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(mult) & 15) == 0;
+    ProfScope prof(SOAP_PROF_EXPAND, s);
+    if (dtype == SOAP_F64)
+      row_inv_norm_kernel<double><<<num_sms() * 8, 256, 0, s>>>(static_cast<const double *>(X), static_cast<const double *>(mult), inv, n_frames, n_atoms, dim, vec_ok);
+    else
+      row_inv_norm_kernel<float><<<num_sms() * 8, 256, 0, s>>>(static_cast<const float *>(X), static_cast<const float *>(mult), inv, n_frames, n_atoms, dim, vec_ok);
+    rc = check_launch("row_inv_norm_kernel");
+    if (rc) return rc;
+    inv_norm = inv;
+  }
   int mult_pitch = 0, plan_dim = dim;
   if (bulk_ok && !whole_units) {
     // rows of 8 mod 16 bytes: every other atom's window starts one word early (tl_item); the plan covers the
@@ -795,8 +875,7 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
     const int lead = 8 / es, ue = 16 / es;
     plan_dim = dim + lead;
     mult_pitch = (plan_dim + ue - 1) / ue * ue + 4 * ue;
-    const size_t total = soap_timelag_scratch_bytes(n_frames, n_atoms, dim, dtype, windows_host, n_windows);
-    void *table = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(static_cast<char *>(scratch) + total - tl_pad_bytes(dim, es)) + 127) & ~(uintptr_t)127);
+    void *table = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(static_cast<char *>(scratch) + scratch_total - tl_pad_bytes(dim, es)) + 127) & ~(uintptr_t)127);
     if (dtype == SOAP_F64)
       shift_mult_kernel<double><<<8, 256, 0, s>>>(static_cast<const double *>(mult), static_cast<double *>(table), dim, mult_pitch, lead);
     else
@@ -829,10 +908,11 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
   if (bulk_ok) bulk_ok |= env_int("SOAP_TL_DIAG", 0) & 30;
 #define TL_CASE(T, NW)                                                                                          \
   case NW:                                                                                                      \
-    rc = mult ? launch_timelag<T, NW, true>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, mult_pitch, s)  \
-              : launch_timelag<T, NW, false>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, mult_pitch, s); \
+    rc = mult ? launch_timelag<T, NW, true>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, mult_pitch, inv_norm, s)  \
+              : launch_timelag<T, NW, false>(X, mult, sc, n_frames, n_atoms, dim, pl, windows_host, kind, bulk_ok, mult_pitch, inv_norm, s); \
     if (rc) return rc;                                                                                          \
-    return launch_finalize<NW>(sc, t, t_offsets_host, n_frames, n_atoms, tl_atom_major(n_atoms) ? 1 : pl.split, windows_host, kind, power, s);
+    return launch_finalize<NW>(sc, t, t_offsets_host, n_frames, n_atoms, tl_atom_major(n_atoms) ? 1 : pl.split, windows_host,     \
+                               kind == SOAP_KIND_EUCLID_NORMALIZED ? SOAP_KIND_EUCLID : kind, power, s);
   if (dtype == SOAP_F64) {
     switch (n_windows) { TL_CASE(double, 1) TL_CASE(double, 2) TL_CASE(double, 3) TL_CASE(double, 4) }
   } else {

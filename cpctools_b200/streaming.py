@@ -135,10 +135,12 @@ def stream_time_soap(dataset, settings: dict, windows, euclid: bool = True, kind
                      power: int = 1, max_block_bytes: int = None):
     """timeSOAP of a chunked compressed dataset for every window in ``windows`` (true lag semantics).
 
-    ``euclid=True``: expand+normalise each block in HBM, then Euclidean distances (the arithmetic of
-    ``timeSOAPsimple``, analysis.py:136).  ``euclid=False``: distances of ``kind`` straight from the
-    compressed block (expansion folded into multiplicities).  Returns CUDA float64 tensors
-    ``[F-w, A]``.
+    ``euclid=True``: the arithmetic of ``timeSOAPsimple`` on ``normalizeArray(fillSOAPVectorFromdscribe(chunk))``
+    (analysis.py:192-200, :136) WITHOUT materialising the expanded vectors: one pass over the compressed block
+    for the norms of the expanded vectors (multiplicity-weighted), then ``|x/|x| - y/|y||`` summed with the
+    multiplicities by the time-lag kernel (``SOAP_KIND_EUCLID_NORMALIZED``): 2 x Dc elements read per vector
+    instead of Dc + 3 x Df.  ``euclid=False``: distances of ``kind`` straight from the compressed block
+    (expansion folded into multiplicities).  Returns CUDA float64 tensors ``[F-w, A]``.
     """
     from .analysis import timelag_device
 
@@ -150,7 +152,7 @@ def stream_time_soap(dataset, settings: dict, windows, euclid: bool = True, kind
         raise ValueError("fillSOAPVectorFromdscribe: the given soap vector do not have the expected dimensions")
     windows = [int(w) for w in windows]
     maxw = max(windows)
-    width = plan.d_full if euclid else Dc
+    width = Dc
     budget = max_block_bytes or MAX_BLOCK_BYTES
     max_frames = max(maxw + 1, budget // max(1, A * width * 8) - maxw)
     outs = [th.empty((F - w, A), dtype=th.float64, device="cuda") for w in windows]
@@ -162,21 +164,12 @@ def stream_time_soap(dataset, settings: dict, windows, euclid: bool = True, kind
         block = th.empty((h + hi - lo, A, width), dtype=raw.dtype, device="cuda")
         if h:
             block[:h].copy_(tail)
-        if euclid:
-            rc = lib.soap_expand_normalize(
-                raw.data_ptr(), block[h:].data_ptr(), plan.index_device().data_ptr(), (hi - lo) * A, Dc,
-                plan.d_full, _device.dtype_code(raw), _device.stream_ptr(),
-            )
-            _lib.check(rc, "soap_expand_normalize")
-        else:
-            block[h:].copy_(raw)
+        block[h:].copy_(raw)
         nb = h + hi - lo
         use = [w for w in windows if w < nb]
         if use:
-            if euclid:
-                res = timelag_device(block, use, _lib.KIND_EUCLID)
-            else:
-                res = timelag_device(block, use, kind, power, mult=plan.multiplicity_device(block.dtype))
+            res = timelag_device(block, use, _lib.KIND_EUCLID_NORMALIZED if euclid else kind, power,
+                                 mult=plan.multiplicity_device(block.dtype))
             for w, tb in zip(use, res):
                 # block-local frame g pairs with g-w; only frames of THIS range (g >= h) are new
                 g0 = max(h, w)

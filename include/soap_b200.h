@@ -39,6 +39,9 @@ enum {
   SOAP_KIND_DOT = 3,        /* kernelSoap(n): the kernel value (x.y/|x||y|)^n, distances.py:38-51 */
   SOAP_KIND_COSCLIP = 4,    /* simpleKernelSoap: 1 - clip(1 - x.y/sqrt(xx yy), 0, 2), distances.py:7-19 */
   SOAP_KIND_EUCLID = 5,     /* |x - y|_2 : the per-frame norm of timeSOAPsimple, analysis.py:136    */
+  SOAP_KIND_EUCLID_NORMALIZED = 7, /* soap_timelag only: |x/|x| - y/|y||_2 with the norms of the EXPANDED vectors taken from
+                                    * the compressed rows and the multiplicities (zero norm -> 1): timeSOAPsimple on
+                                    * normalizeArray(fillSOAPVectorFromdscribe(x)), analysis.py:192-200, without materialising it */
   SOAP_KIND_NORMALIZED_FUSED = 6 /* normalizeArray (utils.py:140-153, zero norm -> 1) folded into
                                SOAPdistanceNormalized: sqrt|2 - 2 x.y/(nx ny)| on RAW vectors   */
 };

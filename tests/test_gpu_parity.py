@@ -483,7 +483,7 @@ def test_large_pageable_arrays_are_staged_in_pieces(S, monkeypatch):
 
     monkeypatch.setattr(_device._HostStager, "MIN_BYTES", 1 << 16)
     monkeypatch.setattr(_device._HostStager, "CHUNK", (1 << 20) + 24)  # several pieces, a ragged last one
-    monkeypatch.setattr(_device, "_stager", None)
+    monkeypatch.setattr(_device, "_stagers", {})  # fresh stagers (pinned buffers of the patched size)
     rng = np.random.default_rng(5)
     for arr in (rng.random((37, 11, 1224)), rng.random((3, 70001)).astype(np.float32), rng.integers(0, 9, (5, 40001))):
         dev = _device.to_device(arr)
@@ -504,14 +504,14 @@ def test_large_pageable_arrays_are_staged_in_pieces(S, monkeypatch):
     attrs, dc = dscribe_attrs(8, 8, ["H", "O"])
     kw = dict(atomTypes=["H", "O"], atomicSlices=_slices_from_attrs(attrs))
     raw = synthetic_soap((40, 9, dc), seed=2, kind="W")
-    monkeypatch.setattr(_device, "_stager", None)
+    monkeypatch.setattr(_device, "_stagers", {})  # fresh stagers (pinned buffers of the patched size)
     got = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1, 5), **kw)
     monkeypatch.setattr(_device._HostStager, "MIN_BYTES", 1 << 40)
     want = S.timeSOAPfromCompressed(raw, 8, 8, windows=(1, 5), **kw)
     for (t1, d1), (t2, d2) in zip(got, want):
         assert_array_equal(t1, t2)
         assert_array_equal(d1, d2)
-    monkeypatch.setattr(_device, "_stager", None)
+    monkeypatch.setattr(_device, "_stagers", {})  # fresh stagers (pinned buffers of the patched size)
 
 
 def test_config1_shape_against_the_loop_oracle(S):
