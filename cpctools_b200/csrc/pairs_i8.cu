@@ -34,7 +34,9 @@ namespace soapb {
 constexpr int kI8BM = 128;
 // epilogue warps per CTA (template parameter EW): two per TMEM lane quarter for fp32; three for fp64, whose
 // long fp64 dependency chains profit from more warps (A/B: 7.78 -> 7.56 ms; fp32 1.83 -> 1.85)
-constexpr int kI8StagePitch = 80;  // bytes per staged row: 64 + 16 pad (16 * odd: conflict-free 128-bit access)
+// bytes per staged row: dense, the 16-byte unit c of row r sits at unit c ^ ((r >> 1) & 3) -- conflict free both for
+// the writes (a lane = a row, all lanes the same c) and for the reads (a quarter warp = 2 rows x 4 units)
+constexpr int kI8StagePitch = 64;
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -52,6 +54,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 // 1.5 * 2^52 (its ulp is 1) and subtract that constant again
 __device__ __forceinline__ double exact_i2d(long long x) {
   return __longlong_as_double(x + 0x4338000000000000ll) - 6755399441055744.0;
+}
+// shared memory by 32-bit address (a generic pointer into the dynamic array compiles to LD.E / ST.E, whose data return
+// through the long-scoreboard path: measured as the largest stall of the epilogue)
+__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4_sync(uint32_t addr) {  // ordered against the st.shared above ("memory")
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -395,6 +412,19 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
           int best_j = -1;
           // one chunk loop, three compile-time flavours of the per-output arithmetic:
           // 0 = lean SOAPdistanceNormalized, 1 = general SOAPdistanceNormalized, 2 = cosine kinds
+          // interior tile: no row / column bound checks on the stores (all but the last tile row / column)
+          const bool interior = vec4 && (long long)(tm + 1) * BM <= M && (long long)(tn + 1) * BN <= N;
+          const uint32_t exp_a = smem_u32(my_exp);
+          const uint32_t stg_a = smem_u32(epi_stage) + (uint32_t)((warp - 2) * (32 * kI8StagePitch));
+          // staged chunk -> global: a lane takes 16 bytes of row 8 m + (lane >> 2); 4 lanes write the 64 contiguous
+          // bytes of a row (a quarter warp touches two rows: fewest cache lines per store pass)
+          const int srow = lane >> 2, cq = (lane & 3) * 4;
+          const uint32_t rd_a = stg_a + (uint32_t)(srow * kI8StagePitch + (((lane & 3) ^ ((srow >> 1) & 3)) << 4));
+          const uint32_t wr_sw = (uint32_t)((lane >> 1) & 3);
+          float *orow[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            orow[m] = reinterpret_cast<float *>(out) + (size_t)((long long)tm * BM + q * 32 + 8 * m + srow) * ldo + (long long)tn * BN + cq;
           auto chunk_loop = [&](auto mode_tag) {
           constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll 1
@@ -405,7 +435,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
             int ej[16];  // lean: the bits of c_j = -2 * 2^(e_j - 1023) as floats; otherwise biased exponents
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const int4 e4 = *reinterpret_cast<const int4 *>(my_exp + c * 16 + j);
+              const int4 e4 = lds_i4(exp_a + (uint32_t)(c * 16 + j) * 4u);
               ej[j] = e4.x; ej[j + 1] = e4.y; ej[j + 2] = e4.z; ej[j + 3] = e4.w;
             }
             tmem_ld_wait();
@@ -414,7 +444,6 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
             // instruction to L2, one per clock (measured: 0.55 of 2.1 ms exposed).  The chunk goes through a
             // padded shared-memory tile instead and leaves as 64 contiguous bytes per row (4 lanes each).
             // (A TMA tile store of the same chunk measured slower: the proxy fence sits on the critical path.)
-            float *stg = reinterpret_cast<float *>(epi_stage + (warp - 2) * (32 * kI8StagePitch));
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               float o[4];
@@ -423,9 +452,11 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                 const int jj = j + k4;
                 const float tf = fmaf(fmaf((float)(int)v[2][jj], 1.0f / 256.0f, (float)(int)v[1][jj]), 1.0f / 256.0f,
                                       (float)(int)v[0][jj]);
+                // (.ftz: the argument is 0 or at least ~2^-46, never subnormal; plain sqrt.approx wraps the MUFU in a
+                // scale / compare / select sequence for subnormals, 4 of the ~30 instructions per output)
                 if constexpr (MODE == 0) {
                   // 2 - 2 g with g = tf * 2^(e_i + e_j): the scaling is exact, so this is the general path's value
-                  asm("sqrt.approx.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(prow * __int_as_float(ej[jj]), tf, 2.0f))));
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(o[k4]) : "f"(fabsf(fmaf(prow * __int_as_float(ej[jj]), tf, 2.0f))));
                 } else {
                   int k = ei + ej[jj] - 2 * 1023;
                   k = k < -126 ? -126 : (k > 127 ? 127 : k);
@@ -444,7 +475,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                   if (col < N && col != row + excl) am_update(o[k4], (int)col, best_v, best_j);
                 }
               }
-              *reinterpret_cast<float4 *>(stg + lane * (kI8StagePitch / 4) + j) = make_float4(o[0], o[1], o[2], o[3]);
+              sts_f4(stg_a + (uint32_t)(lane * kI8StagePitch) + ((((uint32_t)j >> 2) ^ wr_sw) << 4), o[0], o[1], o[2], o[3]);
               if (symmetric && row_ok) {  // out[col][row]: the 32 lanes of a warp write 32 consecutive rows
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
@@ -453,21 +484,27 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
             }
             __syncwarp();
             if (!(debug_flags & 4) && (!AM || out != nullptr)) {
-              const int cq = (lane & 3) * 4;
+              if (interior) {
+                float4 val[4];
 #pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                const int r = 8 * m + (lane >> 2);
-                const long long grow = (long long)tm * BM + q * 32 + r;
-                const float4 val = *reinterpret_cast<const float4 *>(stg + r * (kI8StagePitch / 4) + cq);
-                if (grow < M) {
-                  float *dst = reinterpret_cast<float *>(out) + (size_t)grow * ldo + col0 + cq;
-                  if (vec4 && col0 + cq + 4 <= N) {
-                    *reinterpret_cast<float4 *>(dst) = val;
-                  } else {
-                    if (col0 + cq + 0 < N) dst[0] = val.x;
-                    if (col0 + cq + 1 < N) dst[1] = val.y;
-                    if (col0 + cq + 2 < N) dst[2] = val.z;
-                    if (col0 + cq + 3 < N) dst[3] = val.w;
+                for (int m = 0; m < 4; ++m) val[m] = lds_f4_sync(rd_a + (uint32_t)(8 * m * kI8StagePitch));
+#pragma unroll
+                for (int m = 0; m < 4; ++m) *reinterpret_cast<float4 *>(orow[m] + c * 16) = val[m];
+              } else {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                  const long long grow = (long long)tm * BM + q * 32 + 8 * m + srow;
+                  const float4 val = lds_f4_sync(rd_a + (uint32_t)(8 * m * kI8StagePitch));
+                  if (grow < M) {
+                    float *dst = orow[m] + c * 16;
+                    if (vec4 && col0 + cq + 4 <= N) {
+                      *reinterpret_cast<float4 *>(dst) = val;
+                    } else {
+                      if (col0 + cq + 0 < N) dst[0] = val.x;
+                      if (col0 + cq + 1 < N) dst[1] = val.y;
+                      if (col0 + cq + 2 < N) dst[2] = val.z;
+                      if (col0 + cq + 3 < N) dst[3] = val.w;
+                    }
                   }
                 }
               }
@@ -499,16 +536,28 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
           const double prow = __hiloint2double(ei << 20, 0);  // 2^(e_i - 1023), only used when `lean`
           double best_v = 0.0;
           int best_j = -1;
+          // interior tile: no row / column bound checks on the stores; the per-warp column tables are read by 32-bit
+          // shared addresses (generic pointers compile to LD.E: long-scoreboard latency in front of every DMUL)
+          const bool interior = vec2 && (long long)(tm + 1) * BM <= M && (long long)(tn + 1) * BN <= N;
+          const uint32_t exp_a = smem_u32(my_exp), rn_a = smem_u32(my_rn);
 #pragma unroll 1
           for (int c = part; c < ((debug_flags & 1) ? 0 : BN / 8); c += PARTS) {
             uint32_t v[ND][8];
 #pragma unroll
             for (int g = 0; g < ND; ++g) tmem_ld8(taddr + (uint32_t)(g * BN + c * 8), v[g]);
             int ej[8];
+            double rn[8];
 #pragma unroll
             for (int j = 0; j < 8; j += 4) {
-              const int4 e4 = *reinterpret_cast<const int4 *>(my_exp + c * 8 + j);
+              const int4 e4 = lds_i4(exp_a + (uint32_t)(c * 8 + j) * 4u);
               ej[j] = e4.x; ej[j + 1] = e4.y; ej[j + 2] = e4.z; ej[j + 3] = e4.w;
+            }
+            if (lean || cosine) {
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const double2 r2 = lds_d2(rn_a + (uint32_t)(c * 8 + j) * 8u);
+                rn[j] = r2.x; rn[j + 1] = r2.y;
+              }
             }
             tmem_ld_wait();
             const long long col0 = (long long)tn * BN + c * 8;
@@ -528,14 +577,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                 for (int g = ND / 2; g < ND; ++g) lo = lo * 256 + (long long)(int)v[g][jj];
                 const double tsum = fma(exact_i2d(lo), kLo, exact_i2d(hi) * kHi);
                 if (lean) {  // 2 - 2 g with g = tsum * 2^(e_i + e_j): exact scaling, same value as below
-                  o[k2] = sqrt(fabs(fma(prow * my_rn[c * 8 + jj], tsum, 2.0)));
+                  o[k2] = sqrt(fabs(fma(prow * rn[jj], tsum, 2.0)));
                   continue;
                 }
                 int k = ei + ej[jj] - 2 * 1023;
                 k = k < -1022 ? -1022 : (k > 1023 ? 1023 : k);
                 const double pw = (ei == 0x7ff || ej[jj] == 0x7ff) ? __longlong_as_double(0x7ff8000000000000ll)
                                                                    : __hiloint2double((k + 1023) << 20, 0);
-                o[k2] = cosine ? fast_cosine_distance(tsum * pw, ri * my_rn[c * 8 + jj], kind, power)
+                o[k2] = cosine ? fast_cosine_distance(tsum * pw, ri * rn[jj], kind, power)
                                : sqrt(fabs(fma(-2.0, tsum * pw, 2.0)));
               }
               if constexpr (AM) {
@@ -545,7 +594,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                   if (col < N && col != row + excl) am_update(o[k2], (int)col, best_v, best_j);
                 }
               }
-              if (row_ok && (!AM || out != nullptr)) {
+              if (interior && !symmetric && (!AM || out != nullptr)) {
+                *reinterpret_cast<double2 *>(dst + j) = make_double2(o[0], o[1]);
+              } else if (row_ok && (!AM || out != nullptr)) {
                 if (vec2 && col0 + j + 2 <= N) {
                   *reinterpret_cast<double2 *>(dst + j) = make_double2(o[0], o[1]);
                 } else {
