@@ -178,7 +178,13 @@ constexpr int kI8MaxPanels = 2048;  // symmetric calls: panel offsets live in sh
 // AM: also keep, per row and (tile column, epilogue warp), the minimum over the columns and its index
 // (am_val / am_idx [slot][row], slot = tn * (EW / 4) + part; rowmin_reduce_kernel folds the slots); `out` may
 // then be NULL.  Column row + excl is skipped (the self distance of a row block).
-template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, bool SYM, int EW, bool COS, bool AM, typename OutT>
+// CG = 2: CTA pairs.  The two CTAs of a cluster (the two SMs of a TPC) compute a 256 x BN tile with ONE
+// tcgen05.mma.cta_group::2 per pass, issued by the even CTA: each CTA stages its own 128 rows of A and HALF of the B
+// tile (BN / 2 rows), so an MMA reads A 4 kB + B BN/2 * 32 B per CTA instead of A + the whole B tile -- what made the
+// N = 80 passes of the fp64 kernel shared-memory-operand bound -- and a stage is smaller (one more fits).  TMA loads
+// of both CTAs are counted on the leader's `full` barrier, tcgen05.commit is multicast to the `empty` / `tmem_full`
+// barriers of both, and the epilogue warps of both arrive on the leader's `tmem_empty`.
+template <int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, bool SYM, int EW, bool COS, bool AM, typename OutT, int CG = 1>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
     pairs_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     OutT *__restrict__ out, const double *__restrict__ sa, const double *__restrict__ sb,
@@ -187,13 +193,19 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                     double *__restrict__ am_val, int *__restrict__ am_idx, long long excl) {
   constexpr int BM = kI8BM;
   constexpr int kI8EpiWarps = EW;
-  constexpr int A_PLANE = BM * BKB, B_PLANE = BN * BKB;
+  static_assert(CG == 1 || CG == 2, "CTAs per MMA");
+  static_assert(!(SYM && CG == 2), "the symmetric tile walk is built for single CTAs");
+  constexpr int B_ROWS = BN / CG;  // rows of the B tile staged by this CTA
+  constexpr int A_PLANE = BM * BKB, B_PLANE = B_ROWS * BKB;
   constexpr int STAGE_BYTES = ND * (A_PLANE + B_PLANE);
   constexpr int KS = BKB / 32;  // UMMA K = 32 for 8-bit operands
-  // instruction descriptor: D = s32, A = B = signed int8, K-major, N = BN, M = 128
-  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // instruction descriptor: D = s32, A = B = signed int8, K-major, N = BN, M = 128 (256 for a CTA pair)
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
   static_assert(ACC * ND * BN <= 512, "accumulators exceed TMEM");  // ACC = accumulator sets (2: epilogue overlaps the next tile)
-  static_assert(BN % 16 == 0 && BN <= 256, "invalid UMMA N");
+  static_assert(BN % 16 == 0 && BN <= 256 && (B_ROWS % 8) == 0, "invalid UMMA N");
+  const int crank = CG == 2 ? (int)cluster_ctarank() : 0;            // 0 = leader of the pair
+  const long long work0 = CG == 2 ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;  // first tile of this CTA (pair)
+  const long long work_step = CG == 2 ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -247,7 +259,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
       tn = first + (int)(r % width);
       return (long long)(tn + 1) * BN > (long long)tm * BM;
     }
-    tile_coords_i8(t, tiles_m, tiles_n, tm, tn);
+    tile_coords_i8(t, tiles_m, tiles_n, tm, tn);  // CG == 2: tiles_m counts 256-row tiles
+    tm = tm * CG + crank;
     return true;
   };
 
@@ -258,17 +271,24 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kI8EpiWarps);
+      mbar_init(&tmem_empty[a], kI8EpiWarps * CG);
     }
     fence_mbar_init();
   }
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything is sent to them
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -277,17 +297,29 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (long long t = work0; t < tiles; t += work_step) {
         int tm, tn;
         if (!coords(t, tm, tn)) continue;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait_guard(&empty[s], ph ^ 1);
           unsigned char *st = smem + (size_t)s * STAGE_BYTES;
-          mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+          if constexpr (CG == 2) {
+            // the leader's barrier counts the bytes of both CTAs (a stage is released to both by one multicast
+            // commit, so the peer's loads of this round cannot land before the leader's barrier is in this phase)
+            if (crank == 0) mbar_expect_tx(&full[s], 2u * (uint32_t)STAGE_BYTES);
 #pragma unroll
-          for (int a = 0; a < ND; ++a) {
-            tma_load_2d(st + a * A_PLANE, &map_a, kb * BKB, (int)(a * M + (long long)tm * BM), &full[s]);
-            tma_load_2d(st + ND * A_PLANE + a * B_PLANE, &map_b, kb * BKB, (int)(a * N + (long long)tn * BN), &full[s]);
+            for (int a = 0; a < ND; ++a) {
+              tma_load_2d_pair(st + a * A_PLANE, &map_a, kb * BKB, (int)(a * M + (long long)tm * BM), &full[s]);
+              tma_load_2d_pair(st + ND * A_PLANE + a * B_PLANE, &map_b, kb * BKB,
+                               (int)(a * N + (long long)tn * BN + crank * B_ROWS), &full[s]);
+            }
+          } else {
+            mbar_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
+#pragma unroll
+            for (int a = 0; a < ND; ++a) {
+              tma_load_2d(st + a * A_PLANE, &map_a, kb * BKB, (int)(a * M + (long long)tm * BM), &full[s]);
+              tma_load_2d(st + ND * A_PLANE + a * B_PLANE, &map_b, kb * BKB, (int)(a * N + (long long)tn * BN), &full[s]);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -298,7 +330,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
     int s = 0;
     uint32_t ph = 0;
     int it = 0;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    for (long long t = work0; t < tiles && crank == 0; t += work_step) {  // (a pair's MMAs are issued by its leader)
       {
         int tm, tn;
         if (!coords(t, tm, tn)) continue;
@@ -325,13 +357,22 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
                 const uint32_t pb = st + ND * A_PLANE + b * B_PLANE;
                 const uint64_t db = (BKB == 128 ? umma_desc_sw128(pb) : BKB == 64 ? umma_desc_sw64(pb) : umma_desc_sw32(pb)) + adv;
                 // digit pairs of equal weight a+b share accumulator g = a+b; (0, g) is its first pass
-                if (!(debug_flags & 2) || (a | b | ks) == 0)
-                  tc_mma_i8(tmem_acc + (uint32_t)((a + b) * BN), da, db, IDESC, (kb | ks | a) != 0 ? 1u : 0u);
+                if (!(debug_flags & 2) || (a | b | ks) == 0) {
+                  if constexpr (CG == 2)
+                    tc_mma_i8_pair(tmem_acc + (uint32_t)((a + b) * BN), da, db, IDESC, (kb | ks | a) != 0 ? 1u : 0u);
+                  else
+                    tc_mma_i8(tmem_acc + (uint32_t)((a + b) * BN), da, db, IDESC, (kb | ks | a) != 0 ? 1u : 0u);
+                }
               }
             }
           }
-          tc_commit(&empty[s]);
-          if (kb == KB - 1) tc_commit(&tmem_full[as]);
+          if constexpr (CG == 2) {
+            tc_commit_pair(&empty[s]);
+            if (kb == KB - 1) tc_commit_pair(&tmem_full[as]);
+          } else {
+            tc_commit(&empty[s]);
+            if (kb == KB - 1) tc_commit(&tmem_full[as]);
+          }
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -346,7 +387,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
     constexpr int VEC = 16 / (int)sizeof(OutT);
     const bool vec_ok = ((ldo % VEC) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     int it = -1;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    for (long long t = work0; t < tiles; t += work_step) {
       int tm, tn;
       if (!coords(t, tm, tn)) continue;
       ++it;
@@ -620,9 +661,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
             }
           }
         }
+        // (signalling tmem_empty right after this warp's LAST TMEM read, so that the next tile's MMAs overlap the
+        // arithmetic and stores of the last chunk, measured SLOWER: fp32 block 15.4 against 15.1 ms, fp64 68.2 against
+        // 66.1 -- the kernel runs under the power cap, overlap buys no time there)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]);
+        }
         continue;
       }
       mbar_wait_guard(&tmem_full[as], (uint32_t)((it / ACC) & 1));
@@ -695,15 +741,20 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]);
+        }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // (pair: the leader's MMAs also write the peer's TMEM)
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -745,7 +796,7 @@ struct I8RowMin {
   long long excl;
 };
 
-template <typename InT, int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, int EW, bool COS, typename OutT>
+template <typename InT, int ND, int BN, int BKB, int ACC, int STAGES, bool FAST, int EW, bool COS, typename OutT, int CG = 1>
 static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int64_t N, int D, int64_t ldo, int kind,
                            int power, void *scratch, cudaStream_t s, const I8RowMin *am = nullptr) {
   SOAP_REQUIRE(out != nullptr || am != nullptr, "soap_pairs: the tensor-core path writes the full matrix (out == NULL)");
@@ -776,19 +827,20 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   const CUtensorMapSwizzle swz = BKB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : BKB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap map_a, map_b;
   if ((rc = make_tensor_map_2d(&map_a, pa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * M, Dp, BKB, kI8BM, swz))) return rc;
-  if ((rc = make_tensor_map_2d(&map_b, pb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * N, Dp, BKB, BN, swz))) return rc;
-  const int tiles_m = (int)((M + kI8BM - 1) / kI8BM), tiles_n = (int)((N + BN - 1) / BN);
+  if ((rc = make_tensor_map_2d(&map_b, pb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)ND * N, Dp, BKB, BN / CG, swz))) return rc;
+  // (CTA pairs: a tile is 256 rows, each CTA of the pair stages half of the B tile)
+  const int tiles_m = (int)((M + kI8BM * CG - 1) / (kI8BM * CG)), tiles_n = (int)((N + BN - 1) / BN);
   long long tiles = (long long)tiles_m * tiles_n;
   // data is spectra: d(i,j) == d(j,i) bit for bit (exact integer sums, commutative scaling), so only
   // the tiles that contain some j >= i are computed and every value is stored twice
   // (the upper-triangular tile walk is computed on the device from the tile number: no tile list, no host work
   // and no stream synchronisation per call)
-  const bool sym = FAST && same && am == nullptr && (tiles_n + kI8PanelW - 1) / kI8PanelW <= kI8MaxPanels &&
+  const bool sym = CG == 1 && FAST && same && am == nullptr && (tiles_n + kI8PanelW - 1) / kI8PanelW <= kI8MaxPanels &&
                    getenv("SOAP_I8_NO_SYMMETRY") == nullptr;
   if (sym) tiles = (tiles + 1) / 2 + tiles_m;  // grid sizing only
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   // the reciprocal-norm staging only exists for the cosine kinds (it would not fit beside 4 stages)
-  const size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN) * BKB + 256 + (size_t)EW * BN * 4 +
+  const size_t SMEM = 1024 + (size_t)STAGES * ND * (kI8BM + BN / CG) * BKB + 256 + (size_t)EW * BN * 4 +
                       (FAST ? (size_t)EW * (BN * 8 + 32 * kI8StagePitch) : 0) + (sym ? (size_t)(kI8MaxPanels + 1) * 8 : 0);
   SOAP_REQUIRE(SMEM <= (size_t)max_smem_optin(), "soap_pairs: internal: tile configuration exceeds shared memory");
   constexpr int PARTS = EW / 4;
@@ -800,7 +852,11 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   }
   void (*kern)(CUtensorMap, CUtensorMap, OutT *, const double *, const double *, const double *, const double *, long long,
                long long, int, long long, int, int, int, int, int, double *, int *, long long);
-  if constexpr (FAST) {
+  if constexpr (CG == 2) {
+    static_assert(FAST, "CTA pairs are built for the lean epilogues");
+    kern = am ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, true, false, EW, COS, true, OutT, 2>
+              : pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, true, false, EW, COS, false, OutT, 2>;
+  } else if constexpr (FAST) {
     kern = am ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, true, false, EW, COS, true, OutT>
               : (sym ? pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, true, true, EW, COS, false, OutT>
                      : pairs_i8_kernel<ND, BN, BKB, ACC, STAGES, true, false, EW, COS, false, OutT>);
@@ -810,10 +866,41 @@ static int launch_pairs_i8(const InT *A, const InT *B, OutT *out, int64_t M, int
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   const char *dbg = getenv("SOAP_I8_DEBUG");  // experiments: 1 = skip the epilogue, 2 = one MMA per K block, 4 = no stores
   {
-    ProfScope prof(SOAP_PROF_PAIRS, s);
-    kern<<<grid, 64 + 32 * EW, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, Dp / BKB, ldo, kind, power, tiles_m, tiles_n,
-                                        dbg ? atoi(dbg) : 0, am_val, am_idx, am ? am->excl : 0);
-    rc = check_launch("pairs_i8_kernel");
+    const long long excl = am ? am->excl : 0;
+    const int dbg_flags = dbg ? atoi(dbg) : 0, kb = Dp / BKB;
+    if constexpr (CG == 2) {
+      // one cluster of two CTAs per TPC: as many pairs as the device can hold at once (a GPC with an odd number of
+      // SMs leaves one SM idle), never more than there are tiles
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3(2 * (unsigned)(num_sms() / 2), 1, 1);
+      cfg.blockDim = dim3(64 + 32 * EW, 1, 1);
+      cfg.dynamicSmemBytes = SMEM;
+      cfg.stream = s;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int clusters = 0;
+      SOAP_CUDA(cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg));
+      SOAP_REQUIRE(clusters >= 1, "soap_pairs: no CTA pair fits on this device");
+      if ((long long)clusters > tiles) clusters = (int)tiles;
+      grid = 2 * clusters;
+      cfg.gridDim = dim3((unsigned)grid, 1, 1);
+      ProfScope prof(SOAP_PROF_PAIRS, s);
+      SOAP_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, out, (const double *)sa, (const double *)sb, (const double *)ua,
+                                   (const double *)ub, (long long)M, (long long)N, kb, (long long)ldo, kind, power, tiles_m,
+                                   tiles_n, dbg_flags, am_val, am_idx, excl));
+      rc = check_launch("pairs_i8_kernel (CTA pairs)");
+    } else {
+      ProfScope prof(SOAP_PROF_PAIRS, s);
+      kern<<<grid, 64 + 32 * EW, SMEM, s>>>(map_a, map_b, out, sa, sb, ua, ub, M, N, kb, ldo, kind, power, tiles_m, tiles_n,
+                                          dbg_flags, am_val, am_idx, excl);
+      rc = check_launch("pairs_i8_kernel");
+    }
   }
   if (rc || !am) return rc;
   rowmin_reduce_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(am_val, am_idx, (long long)tiles_n * PARTS, M, am->argmin_out,
@@ -832,6 +919,23 @@ size_t pairs_i8_rowmin_scratch(int64_t M, int64_t N, int D, int dtype) {
 
 #define I8_LAUNCH(IN, ND, BN, BKB, ACC, ST, FAST, EW, COS, OUT) \
   launch_pairs_i8<IN, ND, BN, BKB, ACC, ST, FAST, EW, COS, OUT>(A, B, out, M, N, D, ldo, kind, power, scratch, s, am)
+#define I8_LAUNCH_PAIR(IN, ND, BN, BKB, ACC, ST, EW, COS, OUT) \
+  launch_pairs_i8<IN, ND, BN, BKB, ACC, ST, true, EW, COS, OUT, 2>(A, B, out, M, N, D, ldo, kind, power, scratch, s, am)
+
+// CTA pairs (cta_group::2) are OPT-IN (SOAP_I8_CG=2): bit-identical to single CTAs on every shape tried
+// (scripts/pairs_cg_check.py), but not faster -- 25 000 x 200 000 x 576 block: fp32 15.1 against 14.5 ms, fp64 65.4
+// against 63.8; MMAs alone (25 000^2): fp64 5.32 against 5.41 ms, fp32 1.31 against 1.22.  The N = 80 passes are NOT
+// shared-memory-operand bound as round 1 assumed: halving the B reads per CTA changes nothing, the int8 pipe itself
+// delivers ~5000-6300 MACs/clk/SM here (cuBLASLt IMMA measured in the bench: 5400), not the nominal 8192.  Pairs
+// couple the epilogues of two SMs (the next MMA waits for both), which costs more than the smaller stages give.
+// The symmetric call (data is spectra) keeps its own single-CTA tile walk.
+static bool i8_use_pairs(const void *A, const void *B, int64_t M, int64_t N, const I8RowMin *am) {
+  const char *cg = getenv("SOAP_I8_CG");
+  if (!cg || atoi(cg) != 2) return false;
+  const bool same = (A == B && M == N);
+  const bool sym = same && am == nullptr && getenv("SOAP_I8_NO_SYMMETRY") == nullptr;
+  return !sym && M > kI8BM;
+}
 
 // Tile shapes measured on 25 000^2 x 576 (ms, first version of the epilogue), fp32: N160/K64/4 stages 2.19 |
 // N80/K64/4 stages, 2 accumulator sets 2.33 | N160/K128/2 stages 2.35 | N80/K128/2 stages, 2 sets 2.41;
@@ -846,6 +950,10 @@ int pairs_i8_f32(const float *A, const float *B, float *out, int64_t M, int64_t 
     // N = 80 MMAs are shared-memory-operand bound) instead of one set of N = 160 (experiments, scripts/prof_block.py)
     const char *tile = getenv("SOAP_I8_TILE");
     if (tile && atoi(tile) == 80) return I8_LAUNCH(float, 3, 80, 64, 2, 4, true, 8, false, float);
+    const char *stg = getenv("SOAP_I8_STAGES");  // experiments: smaller operand pipelines
+    if (stg && atoi(stg) == 2) return I8_LAUNCH(float, 3, 160, 64, 1, 2, true, 8, false, float);
+    if (stg && atoi(stg) == 432) return I8_LAUNCH(float, 3, 160, 32, 1, 4, true, 8, false, float);
+    if (i8_use_pairs(A, B, M, N, am)) return I8_LAUNCH_PAIR(float, 3, 160, 64, 1, 4, 8, false, float);
     return I8_LAUNCH(float, 3, 160, 64, 1, 3, true, 8, false, float);
   }
   return I8_LAUNCH(float, 3, 80, 128, 2, 2, false, 8, true, float);
@@ -856,9 +964,13 @@ int pairs_i8_f64(const double *A, const double *B, double *out, int64_t M, int64
   I8RowMin rm{argmin_out, min_out, excl};
   const I8RowMin *am = (argmin_out || min_out) ? &rm : nullptr;
   if (kind == SOAP_KIND_SIMPLE || kind == SOAP_KIND_KERNEL) return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, 12, true, double);
-  if (kind == SOAP_KIND_NORMALIZED) return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, 12, false, double);
+  if (kind == SOAP_KIND_NORMALIZED) {
+    if (i8_use_pairs(A, B, M, N, am)) return I8_LAUNCH_PAIR(double, 6, 80, 64, 1, 3, 12, false, double);
+    return I8_LAUNCH(double, 6, 80, 64, 1, 2, true, 12, false, double);
+  }
   return I8_LAUNCH(double, 6, 80, 64, 1, 2, false, 8, true, double);
 }
 #undef I8_LAUNCH
+#undef I8_LAUNCH_PAIR
 
 }  // namespace soapb

@@ -879,6 +879,34 @@ def test_pairs_tensor_many_tiles_persistent(S):
     assert np.abs(tf32**2 - want32**2).max() <= 5.0e-5
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("M,K,D", [(300, 256, 576), (129, 333, 64), (1000, 1777, 324), (257, 4000, 100)])
+def test_pairs_cta_pairs_equal_single_ctas(S, monkeypatch, dtype, M, K, D):
+    """cta_group::2 (SOAP_I8_CG=2, opt-in): two CTAs share one tcgen05.mma per pass, each staging its own rows of A
+    and half of the B tile.  Same exact integer sums, same epilogue: the matrix and the fused row minima must be
+    BIT-identical to the single-CTA kernel, ragged tiles included (odd 128-row tile counts leave a CTA without rows)."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.classify import pairs_device
+
+    tdt = torch.float32 if dtype == "f32" else torch.float64
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    X = torch.nn.functional.normalize(torch.rand(M, D, dtype=tdt, device="cuda", generator=g) - 0.3, dim=-1)
+    Y = torch.nn.functional.normalize(torch.rand(K, D, dtype=tdt, device="cuda", generator=g) - 0.3, dim=-1)
+    monkeypatch.delenv("SOAP_I8_CG", raising=False)
+    one = pairs_device(X, Y, _lib.KIND_NORMALIZED, 1, path=_lib.PAIRS_TENSOR)
+    am1 = pairs_device(X, Y, _lib.KIND_NORMALIZED, 1, path=_lib.PAIRS_TENSOR, want_argmin=True)
+    monkeypatch.setenv("SOAP_I8_CG", "2")
+    two = pairs_device(X, Y, _lib.KIND_NORMALIZED, 1, path=_lib.PAIRS_TENSOR)
+    am2 = pairs_device(X, Y, _lib.KIND_NORMALIZED, 1, path=_lib.PAIRS_TENSOR, want_argmin=True)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    for a, b in zip(am1, am2):
+        assert torch.equal(a, b)
+    want = torch.sqrt(torch.abs(2.0 - 2.0 * (X.double() @ Y.double().T))).cpu().numpy()
+    assert_distance_parity(two.cpu().numpy(), want, dtype, what="cta pairs")
+
+
 @pytest.mark.parametrize("n", [1000, 1337])
 def test_symmetric_all_pairs_every_kind(S, n):
     """data is spectra: upper-triangular tiles + mirrored stores; ragged sizes, all three kinds, both dtypes."""
