@@ -118,7 +118,7 @@ def pairs_device(data, spectra, kind: int, power: int = 1, path: int = _lib.PAIR
     if want_argmin:
         amin = th.empty(M, dtype=th.float64, device=data.device)
         arg = th.empty(M, dtype=th.int32, device=data.device)
-        tensor = (path != _lib.PAIRS_SIMT and M >= 128 and K >= 256 and M * K >= 1_000_000
+        tensor = (path != _lib.PAIRS_SIMT and M >= 128 and K >= 256 and D >= 32 and M * K >= 1_000_000
                   and kind in (_lib.KIND_SIMPLE, _lib.KIND_KERNEL, _lib.KIND_NORMALIZED))
         if exclude_offset is not None and not tensor:
             raise _lib.SoapB200Error("pairs_device: exclude_offset needs a problem large enough for the tensor-core path")

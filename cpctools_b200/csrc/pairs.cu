@@ -229,7 +229,9 @@ extern "C" int soap_pairs(const void *data, const void *spectra, void *out, int6
                  ">= 128 x 128; no EUCLID)");
     tensor = true;
   } else if (path == SOAP_PAIRS_AUTO) {
-    tensor = !am && scratch != nullptr && tensor_eligible(n_data, n_spectra, dim, kind, dtype, SOAP_PAIRS_TENSOR) &&
+    // (rows shorter than 32 elements stay on the SIMT kernel: nothing to gain from a K block that is mostly padding,
+    // and the per-row fixed-point digits of the int8 path are at the edge of the 1e-6 rule for such short float32 rows)
+    tensor = !am && scratch != nullptr && dim >= 32 && tensor_eligible(n_data, n_spectra, dim, kind, dtype, SOAP_PAIRS_TENSOR) &&
              (double)n_data * (double)n_spectra >= 1.0e6;
   }
   if (tensor && path == SOAP_PAIRS_AUTO) path = SOAP_PAIRS_TENSOR;

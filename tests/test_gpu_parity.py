@@ -1052,3 +1052,92 @@ def test_fuzz_random_shapes_against_oracle(S):
         gotm = S.getDistanceBetween(a, b, S.SOAPdistanceNormalized)
         assert gotm.dtype == dtype
         assert_distance_parity(gotm, O.getDistanceBetween_batched(a.astype(np.float64), b.astype(np.float64)), path, what=f"case {case} matrix")
+
+
+def test_fuzz_tensor_core_pairs_and_row_minima(S):
+    """16 seeded random shapes through the tcgen05 INT8 path (single CTAs and the opt-in CTA pairs): ragged tile
+    edges in both directions, odd dimensions (K padded to the block), rows of very different magnitude, some signed
+    entries (the digit planes are fixed point per ROW: the error of a dot is ~2^-23 max|x| max|y| sqrt(D), so strongly
+    short float32 rows are at the edge of the 1e-6 rule -- uniform(-0.1, 0.9) rows of D = 11 reach 1.06e-6 on d -- and
+    the automatic dispatch keeps rows under 32 elements on the SIMT kernel); the matrix against the oracle, the fused row minima against numpy on the matrix the same path wrote,
+    with and without an excluded diagonal."""
+    import os
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.classify import pairs_device
+
+    rng = np.random.default_rng(77)
+    names = ["normalized", "simple", "kernel2"]
+    for case in range(16):
+        M, K, D = int(rng.integers(128, 900)), int(rng.integers(256, 1500)), int(rng.integers(32, 700))
+        dtype = [np.float64, np.float32][case % 2]
+        name = names[case % 3]
+        fn, okind, power = _kinds(S)[name]
+        a, b = rng.random((M, D)) - 0.1, rng.random((K, D)) - 0.1
+        a[int(rng.integers(0, M))] *= 1.0e-4
+        b[int(rng.integers(0, K))] *= 3.0e3
+        if name == "normalized":
+            a, b = O.normalizeArray(a), O.normalizeArray(b)
+        a, b = a.astype(dtype), b.astype(dtype)
+        ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        want = O.getDistanceBetween_batched(a.astype(np.float64), b.astype(np.float64), okind, power)
+        prev = os.environ.pop("SOAP_I8_CG", None)
+        try:
+            if case % 4 == 3:
+                os.environ["SOAP_I8_CG"] = "2"
+            full = pairs_device(ad, bd, _lib_kind(name), power, path=_lib.PAIRS_TENSOR).cpu().numpy()
+            assert_distance_parity(full, want, "f64" if dtype == np.float64 else "f32", what=f"case {case} {name} {M}x{K}x{D}")
+            if M * K >= 1_000_000:  # (smaller problems take the SIMT minimum)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    amin, arg = pairs_device(ad, bd, _lib_kind(name), power, want_argmin=True)
+                    assert_array_equal(arg.cpu().numpy(), np.argmin(full, axis=-1))
+                    assert_array_equal(amin.cpu().numpy(), np.amin(full, axis=-1).astype(np.float64))
+                    off = int(rng.integers(0, max(1, K - M)))
+                    amin2, arg2 = pairs_device(ad, bd, _lib_kind(name), power, want_argmin=True, exclude_offset=off)
+                    masked = full.astype(np.float64).copy()
+                    rows = np.arange(M)
+                    keep = rows + off < K
+                    masked[rows[keep], rows[keep] + off] = np.inf
+                    assert_array_equal(arg2.cpu().numpy(), np.argmin(masked, axis=-1))
+                    assert_array_equal(amin2.cpu().numpy(), np.amin(masked, axis=-1))
+        finally:
+            os.environ.pop("SOAP_I8_CG", None)
+            if prev is not None:
+                os.environ["SOAP_I8_CG"] = prev
+
+
+def test_fuzz_timelag_raw_dimensions_and_kinds(S):
+    """30 seeded random trajectories of ARBITRARY row length (odd, 8- and 16-byte multiples alike: the TMA path, the
+    shifted-window path and the element-copy path), every distance kind, one to four windows, both dtypes,
+    with and without multiplicities, against the batched oracle."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.analysis import timelag_device
+
+    rng = np.random.default_rng(4242)
+    kinds = [("simple", _lib.KIND_SIMPLE, O.KIND_SIMPLE, 1), ("kernel1", _lib.KIND_KERNEL, O.KIND_KERNEL, 1),
+             ("kernel2", _lib.KIND_KERNEL, O.KIND_KERNEL, 2), ("normalized", _lib.KIND_NORMALIZED, O.KIND_NORMALIZED, 1)]
+    for case in range(30):
+        F, A, D = int(rng.integers(2, 140)), int(rng.integers(1, 200)), int(rng.integers(1, 420))
+        dtype = [np.float64, np.float32][case % 2]
+        path = "f64" if dtype == np.float64 else "f32_timelag"
+        name, kind, okind, power = kinds[case % 4]
+        X = (rng.random((F, A, D)) + 0.05).astype(dtype)
+        X64 = X.astype(np.float64)
+        if name == "normalized":
+            X64 = O.normalizeArray(X64)
+            X = X64.astype(dtype)
+            X64 = X.astype(np.float64)
+        nw = int(rng.integers(1, 5))
+        windows = tuple(sorted(set(int(w) for w in rng.integers(1, F, size=nw))))
+        use_mult = case % 3 == 0
+        m = (1.0 + (rng.random(D) < 0.5)).astype(dtype) if use_mult else None
+        ts = timelag_device(torch.from_numpy(X).cuda(), windows, kind, power,
+                            mult=None if m is None else torch.from_numpy(m).cuda())
+        Xw = X64 if m is None else X64 * np.sqrt(m.astype(np.float64))
+        for w, t in zip(windows, ts):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want, _ = O.timeSOAP_batched(Xw, window=w, kind=okind, power=power)
+            assert_distance_parity(t.cpu().numpy(), want, path, what=f"case {case} {name} F{F} A{A} D{D} w{w}")
