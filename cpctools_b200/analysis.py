@@ -48,11 +48,12 @@ def timelag_device(X, windows, kind: int, power: int = 1, mult=None):
     F, A, D = (int(s) for s in X.shape)
     windows = [int(w) for w in windows]
     es = X.element_size()
-    tma_rows = (D * es) % 16 == 0 or ((D * es) % 8 == 0 and (A * D * es) % 16 == 0 and X.data_ptr() % 16 == 0)
+    tma_rows = (D * es) % 16 == 0 or ((A * D * es) % 16 == 0 and X.data_ptr() % 16 == 0)
     if not tma_rows and F * A > 4096:
-        # rows that are neither 16-byte multiples nor 8-byte multiples in 16-byte-multiple frames cannot be
-        # fetched by the TMA engine (the kernel would fall back to element-wise cp.async staging, ~0.15 of the
-        # HBM peak): when memory allows, pad the rows once on the device (one extra read + write pass)
+        # the TMA engine fetches rows of any length as long as a FRAME is a whole number of 16-byte units (an atom's
+        # window then starts at the unit boundary below its row, foreign elements masked).  Otherwise the kernel
+        # would fall back to element-wise cp.async staging (~0.15 of the HBM peak): when memory allows, pad the
+        # rows once on the device instead (one extra read + write pass)
         unit = 16 // es
         Dp = (D + unit - 1) // unit * unit
         free, _ = th.cuda.mem_get_info()

@@ -274,10 +274,11 @@ __device__ __forceinline__ double ld_acc(const double *p, uint64_t pol) {
 // consecutive items of the same CTA, so that the reducer can add the pieces up before anything goes to DRAM.
 // Otherwise (few atoms: fewer atoms than would keep every SM busy) items (atom, piece) are dealt round robin
 // and every piece writes its own partial sums, which the finalize kernel adds.
-// `shifted` (rows of 8 mod 16 bytes): the TMA engine wants 16-byte aligned box rows, so the window of an atom whose
-// row starts on an odd 8-byte word begins one word EARLIER; its first unit then carries `lead` foreign elements, or
-// its last unit ends with foreign elements.  The multiplicity table has one variant per shift, zero on the foreign
-// elements, and the consumers clean those units (CLEAN).
+// `shifted` (rows that are not 16-byte multiples): the TMA engine wants 16-byte aligned box rows (a box that starts
+// 4 or 8 bytes into a unit raises an illegal-instruction fault, scripts/micro/tma_align.cu), so the window of an atom
+// whose row starts inside a unit begins at the unit boundary below it; its first unit then carries `lead` foreign
+// elements, and / or its last unit ends with foreign elements.  The multiplicity table has one variant per lead
+// (0 .. UE-1 elements), zero on the foreign elements, and the consumers clean those units (CLEAN).
 template <int UE>
 __device__ __forceinline__ TlItem tl_item(int j, int split, int upp, int D, bool atom_major, bool shifted = false) {
   TlItem it;
@@ -291,12 +292,12 @@ __device__ __forceinline__ TlItem tl_item(int j, int split, int upp, int D, bool
     it.p = (int)(i - it.a * split);
   }
   constexpr int ES = 16 / UE;
-  const long long sw = it.a * D * ES / 8;  // first word of the row (rows are whole words on this path)
-  it.lead = (shifted && (sw & 1)) ? 8 / ES : 0;
+  const long long s0 = it.a * D;                 // first element of the row
+  it.lead = shifted ? (int)(s0 % UE) : 0;        // elements between the 16-byte boundary below the row and the row
   it.e0 = it.p * upp * UE;                       // relative to the (aligned) window
   it.pe = min(it.lead + D - it.e0, upp * UE);    // elements of this piece; <= 0 for an empty last piece
   it.punits = it.pe > 0 ? (it.pe + UE - 1) / UE : 0;
-  it.w0 = sw - (it.lead ? 1 : 0) + (long long)it.e0 * ES / 8;
+  it.w0 = (s0 - it.lead + it.e0) * ES / 8;       // (a whole number of units: an even word)
   return it;
 }
 
@@ -358,8 +359,8 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1)
       const TlItem it = tl_item<UE>(k, split, upp, D, atom_major, (bulk_ok & 32) != 0);
       const T *xa = X + (size_t)it.a * D + it.e0;
       const int mslot = k & (mbuf - 1);
-      // shifted rows: one multiplicity table per shift ([2][mult_pitch] elements)
-      const T *mrow = mult + ((bulk_ok & 32) && it.lead ? mult_pitch : 0) + it.e0;
+      // shifted rows: one multiplicity table per lead ([UE][mult_pitch] elements)
+      const T *mrow = mult + ((bulk_ok & 32) ? it.lead * mult_pitch : 0) + it.e0;
       for (int b = 0; b < nblk; ++b, ++g) {
         if (g >= back) {
           mbar_wait(&empty[js], (uint32_t)jph);
@@ -713,12 +714,12 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// shifted rows: table[ph][i] = multiplicity of element i - ph * lead of the row (ones when the caller passes none),
+// shifted rows: table[lead][i] = multiplicity of element i - lead of the row (ones when the caller passes none),
 // zero outside the row -- what masks the foreign elements of the first / last unit of an atom's window
 template <typename T>
-__global__ void shift_mult_kernel(const T *__restrict__ mult, T *__restrict__ out, int D, int pitch, int lead) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * pitch; i += gridDim.x * blockDim.x) {
-    const int ph = i / pitch, e = i - ph * pitch - ph * lead;
+__global__ void shift_mult_kernel(const T *__restrict__ mult, T *__restrict__ out, int D, int pitch, int n_leads) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_leads * pitch; i += gridDim.x * blockDim.x) {
+    const int lead = i / pitch, e = i - lead * pitch - lead;
     out[i] = (e >= 0 && e < D) ? (mult ? mult[e] : (T)1) : (T)0;
   }
 }
@@ -796,7 +797,7 @@ static int launch_finalize(const double *scratch, double *t, const int64_t *off,
 using namespace soapb;
 
 // room at the end of the scratch area for the zero-padded multiplicities (rows that are not whole units)
-static size_t tl_pad_bytes(int dim, int es) { return 2 * ((size_t)dim + 32) * es + 256; }
+static size_t tl_pad_bytes(int dim, int es) { return 4 * ((size_t)dim + 32) * es + 256; }
 // ... and, before it, for the reciprocal row norms of SOAP_KIND_EUCLID_NORMALIZED
 static size_t tl_inv_bytes(int64_t F, int64_t A) { return (size_t)F * A * sizeof(double) + 256; }
 
@@ -823,7 +824,7 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
                8 * rp.mult_elems * es + 256;
   }
   TimelagPlan pl;
-  const int plan_dim = (((size_t)dim * es) % 16 != 0 && ((size_t)dim * es) % 8 == 0) ? dim + 8 / es : dim;  // shifted rows
+  const int plan_dim = ((size_t)dim * es) % 16 != 0 ? dim + 16 / es - 1 : dim;  // shifted rows: the widest window
   if (!make_plan(n_frames, plan_dim, es, windows_host, n_windows, pl))
     return rb_bytes + tl_pad_bytes(dim, es) + tl_inv_bytes(n_frames, n_atoms);
   // totals sums[a][q][f] + one accumulator [q][frames padded to 32] per resident CTA
@@ -844,11 +845,12 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
   int rc = check_windows(n_frames, windows_host, n_windows, "soap_timelag");
   if (rc) return rc;
   const int es = dtype == SOAP_F64 ? 8 : 4;
-  // TMA path: 16-byte aligned base pointers, rows of whole 8-byte words and frames of whole 16-byte units (the
-  // tensor map counts 8-byte words; a row that ends in half a unit -- fp32, D = 4k + 2 -- has that unit masked)
+  // TMA path: 16-byte aligned base pointers and frames of whole 16-byte units (the tensor map counts 8-byte words);
+  // rows need not be whole units: a window then starts at the unit boundary below its row and the foreign elements
+  // of its first / last unit are masked (tl_item)
   const bool whole_units = ((size_t)dim * es) % 16 == 0;
-  int bulk_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (((size_t)dim * es) % 8 == 0) &&
-                (((size_t)n_atoms * dim * es) % 16 == 0) && ((reinterpret_cast<uintptr_t>(mult) & 15) == 0);
+  int bulk_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (((size_t)n_atoms * dim * es) % 16 == 0) &&
+                ((reinterpret_cast<uintptr_t>(mult) & 15) == 0);
   auto s = static_cast<cudaStream_t>(stream);
   auto sc = static_cast<double *>(scratch);
   const size_t scratch_total = soap_timelag_scratch_bytes(n_frames, n_atoms, dim, dtype, windows_host, n_windows);
@@ -870,16 +872,16 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
   }
   int mult_pitch = 0, plan_dim = dim;
   if (bulk_ok && !whole_units) {
-    // rows of 8 mod 16 bytes: every other atom's window starts one word early (tl_item); the plan covers the
-    // widest window, the multiplicities become a [2][pitch] table that is zero on the foreign elements
-    const int lead = 8 / es, ue = 16 / es;
-    plan_dim = dim + lead;
+    // rows that are not whole units: an atom's window starts up to ue - 1 elements early (tl_item); the plan covers
+    // the widest window, the multiplicities become a [ue][pitch] table that is zero on the foreign elements
+    const int ue = 16 / es;
+    plan_dim = dim + ue - 1;
     mult_pitch = (plan_dim + ue - 1) / ue * ue + 4 * ue;
     void *table = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(static_cast<char *>(scratch) + scratch_total - tl_pad_bytes(dim, es)) + 127) & ~(uintptr_t)127);
     if (dtype == SOAP_F64)
-      shift_mult_kernel<double><<<8, 256, 0, s>>>(static_cast<const double *>(mult), static_cast<double *>(table), dim, mult_pitch, lead);
+      shift_mult_kernel<double><<<8, 256, 0, s>>>(static_cast<const double *>(mult), static_cast<double *>(table), dim, mult_pitch, ue);
     else
-      shift_mult_kernel<float><<<8, 256, 0, s>>>(static_cast<const float *>(mult), static_cast<float *>(table), dim, mult_pitch, lead);
+      shift_mult_kernel<float><<<8, 256, 0, s>>>(static_cast<const float *>(mult), static_cast<float *>(table), dim, mult_pitch, ue);
     rc = check_launch("shift_mult_kernel");
     if (rc) return rc;
     mult = table;

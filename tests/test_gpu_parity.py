@@ -283,8 +283,13 @@ def test_timesoap_sweep_from_compressed_vs_oracle(S, F, A, species, dtype, windo
         (41, 601, 612, np.float32, (2, 40)),
         (64, 450, 1198, np.float32, (1, 5, 10, 50)),  # raw quippy fp32 rows: 8- but not 16-byte multiples, TMA + masked tail unit
         (40, 6, 6, np.float32, (1, 3)),       # the same with rows shorter than two units
-        (35, 5, 7, np.float64, (2, 4)),       # unaligned rows: element-copy path, several items per CTA
-        (35, 300, 7, np.float32, (1, 9)),
+        (35, 5, 7, np.float64, (2, 4)),       # unaligned rows AND frames: element-copy path, several items per CTA
+        (35, 300, 7, np.float32, (1, 9)),     # rows of 28 bytes in frames of whole units: TMA, leads 0..3 floats
+        (64, 448, 1197, np.float32, (1, 5, 10, 50)),  # dscribe 3 species n = l = 6 in fp32: odd rows, pieces + leads
+        (50, 1000, 147, np.float32, (1, 5)),  # odd rows, atom-major mode
+        (37, 6, 9, np.float64, (1, 4)),       # fp64 odd rows (72 bytes), even atom count
+        (33, 12, 5, np.float32, (2,)),        # rows shorter than two units with every lead
+        (33, 3, 5, np.float32, (2,)),         # ... and a frame that is NOT a whole unit: element-copy path
     ],
 )
 def test_timelag_persistent_stream_edge_shapes(S, F, A, D, dtype, windows, monkeypatch):
@@ -377,18 +382,22 @@ def test_timelag_register_blocked_kernel(S, F, A, D, dtype, windows, monkeypatch
         assert_distance_parity(np.delete(got, 1, axis=1), np.delete(weighted[0], 1, axis=1), path, what="NaN neighbour")
 
 
-def test_timelag_rows_ending_in_half_a_unit_do_not_leak_the_next_row(S):
-    """fp32 rows of 4k + 2 floats (raw quippy: 1198) go through the TMA path with the last 16-byte unit half
-    foreign: a NaN / huge neighbour must not change an atom's result (and poisons only itself)."""
+@pytest.mark.parametrize("D,dtype", [(1198, np.float32), (1197, np.float32), (147, np.float32), (7, np.float32), (1197, np.float64)])
+def test_timelag_rows_ending_in_half_a_unit_do_not_leak_the_next_row(S, D, dtype):
+    """Rows that are not whole 16-byte units (raw quippy fp32: 1198 floats; dscribe 3 species n = l = 6: 1197) go
+    through the TMA path with windows that start at the unit boundary below the row: the first and / or last unit of
+    an atom carries elements of its neighbours.  A NaN / huge neighbour must not change an atom's result (and
+    poisons only itself)."""
     import torch
     from cpctools_b200 import _lib
     from cpctools_b200.analysis import timelag_device
 
     rng = np.random.default_rng(5)
-    X = rng.random((50, 8, 1198)).astype(np.float32)
+    X = rng.random((50, 8, D)).astype(dtype)
     base = [t.cpu().numpy() for t in timelag_device(torch.from_numpy(X).cuda(), (1, 7), _lib.KIND_SIMPLE, 1)]
     for w, t in zip((1, 7), base):
-        assert_distance_parity(t, O.timeSOAP_batched(X.astype(np.float64), window=w, kind=O.KIND_SIMPLE)[0], "f32_timelag")
+        assert_distance_parity(t, O.timeSOAP_batched(X.astype(np.float64), window=w, kind=O.KIND_SIMPLE)[0],
+                               "f32_timelag" if dtype == np.float32 else "f64")
     Xn = X.copy()
     Xn[:, 3, :] = np.nan
     got = [t.cpu().numpy() for t in timelag_device(torch.from_numpy(Xn).cuda(), (1, 7), _lib.KIND_SIMPLE, 1)]
