@@ -154,17 +154,23 @@ __global__ void __launch_bounds__(kExpandThreads, 2)
     bulk_g2s(stage(s), in + (size_t)t * tv * in_stride, bytes, &bar[s]);
   };
 
+  // bulk_ok bit 1: tiles are staged by bulk copies -- rows need not be 16-byte multiples for that, only TILES (the
+  // host picks tv so that a full tile is; a ragged last tile whose byte count is not falls back to the plain copy);
+  // bit 0: every row is a whole number of 16-byte chunks (vector reads inside the stage)
+  const bool stage_bulk = (bulk_ok & 2) != 0;
+  bulk_ok &= 1;
+  auto tile_bulk = [&](long long tt) { return stage_bulk && (((size_t)tile_rows(tt) * in_stride * sizeof(T)) & 15) == 0; };
   long long t = blockIdx.x;
   int s = 0;
   uint32_t phase_bits = 0;  // bit s = parity of the next completion of bar[s]
-  if (bulk_ok && tid == 0 && t < ntiles) issue(t, 0);
+  if (tid == 0 && t < ntiles && tile_bulk(t)) issue(t, 0);
 
   for (; t < ntiles; t += gridDim.x, s ^= 1) {
     const int rows = tile_rows(t);
-    if (bulk_ok) {
-      const long long tn = t + gridDim.x;
-      // stage s^1 was last read in the previous iteration (trailing __syncthreads below)
-      if (tid == 0 && tn < ntiles) issue(tn, s ^ 1);
+    const long long tn = t + gridDim.x;
+    // stage s^1 was last read in the previous iteration (trailing __syncthreads below)
+    if (tid == 0 && tn < ntiles && tile_bulk(tn)) issue(tn, s ^ 1);
+    if (tile_bulk(t)) {
       mbar_wait(&bar[s], (phase_bits >> s) & 1u);
       phase_bits ^= 1u << s;
     } else {
@@ -342,14 +348,27 @@ static int launch_expand(const void *in, void *out, const int32_t *idx, int64_t 
   int tv = (int)(tile_bytes / row_bytes);
   if (tv < 1) tv = 1;
   if (tv > 64) tv = 64;
-  if ((int64_t)tv > nvec) tv = (int)nvec;
-  const size_t stage_bytes = (((size_t)tv * row_bytes) + 127) & ~(size_t)127;
+  // rows that are not 16-byte multiples (fp32 quippy rows: 1198 floats; odd dscribe rows): a tile of 2 or 4 rows is
+  // one, so tiles can still be staged by bulk copies -- tv becomes a multiple of that row count
+  const int row_mult = row_bytes % 16 == 0 ? 1 : (row_bytes % 8 == 0 ? 2 : (row_bytes % 4 == 0 ? 4 : 0));
   const int d_pad = (d_full + 3) & ~3;
-  const size_t smem = 2 * stage_bytes + (idx ? (size_t)d_pad * 4 : 0) + ((NORM && idx && sizeof(T) == 4) ? (size_t)((in_stride + 3) & ~3) * sizeof(T) : 0) + 2 * ((tv + 1) & ~1) * 8 + (size_t)tv * kMaxSplit * 8 + 16;
+  auto smem_for = [&](int rows) {
+    const size_t stage_bytes = (((size_t)rows * row_bytes) + 127) & ~(size_t)127;
+    return 2 * stage_bytes + (idx ? (size_t)d_pad * 4 : 0) + ((NORM && idx && sizeof(T) == 4) ? (size_t)((in_stride + 3) & ~3) * sizeof(T) : 0) +
+           2 * ((rows + 1) & ~1) * 8 + (size_t)rows * kMaxSplit * 8 + 16;
+  };
+  if (row_mult > 1) {
+    const int tv_al = tv >= row_mult ? tv / row_mult * row_mult : row_mult;
+    if (smem_for(tv_al) <= (size_t)max_smem_optin()) tv = tv_al;  // (very long rows: keep one row per tile, plain copies)
+  }
+  if ((int64_t)tv > nvec) tv = (int)nvec;
+  const size_t smem = smem_for(tv);
   if (smem > (size_t)max_smem_optin())
     return set_error(SOAP_EUNSUPPORTED, "soap_expand: a single vector of %zu bytes does not fit in shared memory",
                      row_bytes);
-  const int bulk_ok = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (row_bytes % 16 == 0);
+  const bool in_aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  const int bulk_ok = ((in_aligned && row_bytes % 16 == 0) ? 1 : 0) |
+                      ((in_aligned && row_mult > 0 && ((size_t)tv * row_bytes) % 16 == 0) ? 2 : 0);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                      (((size_t)d_full * sizeof(T)) % 16 == 0);
   const int64_t ntiles = (nvec + tv - 1) / tv;
