@@ -12,6 +12,12 @@ namespace soapb {
 constexpr int kTrThreads = 256;
 constexpr int kTrMaxShared = 8192;  // class pairs kept in shared memory (90 x 90 classes)
 
+// A thread owns an atom and walks its frame steps.  Slow dynamics means long runs of the SAME transition (mostly
+// i -> i): the thread counts the run in a register and touches the histogram only when the transition changes -- no
+// warp vote, no atomic per step (the first version elected one lane per distinct cell with __match_any_sync every
+// step: 0.22 of the HBM peak on the bytes actually moved).  With window == stride the `from` state of a step is the
+// `to` state of the previous one and stays in a register: every state is read once.
+template <bool CHAIN>  // CHAIN: window == stride
 __global__ void __launch_bounds__(kTrThreads)
     transition_counts_kernel(const int *__restrict__ states, long long n_frames, long long n_atoms, int n_classes,
                              long long window, long long stride, unsigned long long *__restrict__ counts) {
@@ -26,38 +32,53 @@ __global__ void __launch_bounds__(kTrThreads)
   const long long n_steps = (n_frames - window + stride - 1) / stride;
   const long long per_y = (n_steps + gridDim.y - 1) / gridDim.y;
   const long long s0 = (long long)blockIdx.y * per_y, s1 = min(n_steps, s0 + per_y);
-  auto count = [&](int from, int to) {
-    const bool ok = (unsigned)from < (unsigned)n_classes && (unsigned)to < (unsigned)n_classes;
-    // neighbouring atoms mostly make the same transition (few classes, slow dynamics): the lanes of a warp
-    // that hit the same cell elect one of them to add their count (one atomic per distinct cell per warp)
-    const int key = ok ? from * n_classes + to : -1;
-    const unsigned same = __match_any_sync(__activemask(), key);
-    if (ok && (int)(__ffs(same) - 1) == (int)(threadIdx.x & 31)) {
-      if (use_smem)
-        atomicAdd(&hist[key], (unsigned)__popc(same));
-      else
-        atomicAdd(&counts[key], (unsigned long long)__popc(same));
-    }
-  };
-  for (long long atom = (long long)blockIdx.x * kTrThreads + threadIdx.x; atom < n_atoms;
+  for (long long atom = (long long)blockIdx.x * kTrThreads + threadIdx.x; atom < n_atoms && s0 < s1;
        atom += (long long)gridDim.x * kTrThreads) {
-    constexpr int kBatch = 4;  // independent loads in flight per thread
+    int last_key = -1;
+    unsigned run = 0;
+    auto flush = [&]() {
+      if (run && last_key >= 0) {
+        if (use_smem)
+          atomicAdd(&hist[last_key], run);
+        else
+          atomicAdd(&counts[last_key], (unsigned long long)run);
+      }
+    };
+    auto count = [&](int from, int to) {
+      const bool ok = (unsigned)from < (unsigned)n_classes && (unsigned)to < (unsigned)n_classes;
+      const int key = ok ? from * n_classes + to : -1;
+      if (key != last_key) {
+        flush();
+        last_key = key;
+        run = 0;
+      }
+      ++run;
+    };
+    constexpr int kBatch = 8;  // independent loads in flight per thread
+    const int *col = states + atom;
+    int prev = CHAIN ? col[(window + s0 * stride - window) * n_atoms] : 0;
     long long s = s0;
     for (; s + kBatch <= s1; s += kBatch) {
       int from[kBatch], to[kBatch];
 #pragma unroll
       for (int j = 0; j < kBatch; ++j) {
         const long long frame = window + (s + j) * stride;
-        from[j] = states[(frame - window) * n_atoms + atom];
-        to[j] = states[frame * n_atoms + atom];
+        to[j] = col[frame * n_atoms];
+        if (!CHAIN) from[j] = col[(frame - window) * n_atoms];
       }
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) count(from[j], to[j]);
+      for (int j = 0; j < kBatch; ++j) {
+        count(CHAIN ? prev : from[j], to[j]);
+        prev = to[j];
+      }
     }
     for (; s < s1; ++s) {
       const long long frame = window + s * stride;
-      count(states[(frame - window) * n_atoms + atom], states[frame * n_atoms + atom]);
+      const int to = col[frame * n_atoms];
+      count(CHAIN ? prev : col[(frame - window) * n_atoms], to);
+      prev = to;
     }
+    flush();
   }
   if (use_smem) {
     __syncthreads();
@@ -100,8 +121,12 @@ __global__ void __launch_bounds__(256)
       time = 0;
     }
   };
-  // the walk is a dependent chain only through `state`: 8 frames are fetched at once so that a thread
-  // keeps 8 loads in flight (one load per step leaves the memory system ~6 % busy)
+  // the walk is a dependent chain only through `state`: 8 frames are fetched at once so that a thread keeps 8
+  // loads in flight (one load per step leaves the memory system ~6 % busy; 16 measured slower, 0.42 against 0.30 ms
+  // for 2000 x 100 000 states).  emit() adds the CONSTANT 1 to the cursor, which the compiler turns into one atomic
+  // per warp (vote + elect); reserving the slots of a whole batch with one variable-size atomic per thread defeats
+  // that and measured 20x slower (8.7 M same-address atomics).  With one series per atom the kernel is limited by
+  // the number of series (100 000 threads keep ~20 kB per SM in flight), not by the arithmetic.
   constexpr int kBatch = 8;
   long long f = window + initial;
   for (; f + (kBatch - 1) * window < n_frames; f += kBatch * window) {
@@ -163,7 +188,11 @@ extern "C" int soap_transition_counts(const int32_t *states, int64_t n_frames, i
   int64_t gy = (cap + gx - 1) / gx;  // enough CTAs to fill the device; every CTA flushes one histogram
   gy = gy > n_steps ? n_steps : gy;
   gy = gy < 1 ? 1 : (gy > 65535 ? 65535 : gy);
-  transition_counts_kernel<<<dim3((unsigned)gx, (unsigned)gy), kTrThreads, smem, s>>>(
-      states, n_frames, n_atoms, n_classes, window, stride, reinterpret_cast<unsigned long long *>(counts));
+  if (window == stride)
+    transition_counts_kernel<true><<<dim3((unsigned)gx, (unsigned)gy), kTrThreads, smem, s>>>(
+        states, n_frames, n_atoms, n_classes, window, stride, reinterpret_cast<unsigned long long *>(counts));
+  else
+    transition_counts_kernel<false><<<dim3((unsigned)gx, (unsigned)gy), kTrThreads, smem, s>>>(
+        states, n_frames, n_atoms, n_classes, window, stride, reinterpret_cast<unsigned long long *>(counts));
   return check_launch("transition_counts_kernel");
 }

@@ -164,7 +164,8 @@ def main():
             return e0.elapsed_time(e1) / reps
 
         ms = events(lambda: _lib.check(lib.soap_transition_counts(states.data_ptr(), F, A, K, 1, 1, counts.data_ptr(), None)))
-        report("transition_counts", f"{F}x{A} int32 states, {K} classes, window 1", ms, 2 * (F - 1) * A * 4, pairs_per_s=(F - 1) * A / ms * 1e3)
+        report("transition_counts", f"{F}x{A} int32 states, {K} classes, window 1", ms, F * A * 4, pairs_per_s=(F - 1) * A / ms * 1e3,
+               note="bytes = every state once (window == stride: the `from` state of a step is the previous `to`); round 1 counted both reads")
         cap = int(lib.soap_residence_capacity(F, A, 1, 1))
         ev_s = torch.empty(cap, dtype=torch.int32, device="cuda")
         ev_t = torch.empty(cap, dtype=torch.int64, device="cuda")
