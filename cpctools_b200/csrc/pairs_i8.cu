@@ -621,7 +621,10 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1)
             tmem_ld_wait();
             const long long col0 = (long long)tn * BN + c * 8;
             // (staging this chunk through shared memory like the fp32 one measured slower: the fp64 epilogue is
-            // bound by its arithmetic, the stores cost 0.3 of 7.8 ms)
+            // bound by its arithmetic, the stores cost 0.3 of 7.8 ms.  A branch-free square root -- hardware
+            // reciprocal square root + two coupled Newton steps instead of the IEEE routine, whose special-case
+            // branch keeps the eight outputs of a chunk from being interleaved -- measured 63.5 against 63.7 ms for
+            // the bench block: not worth giving up the correctly rounded result)
             double *dst = reinterpret_cast<double *>(out) + (size_t)row * ldo + col0;
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
