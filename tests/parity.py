@@ -7,23 +7,25 @@ The reference itself returns 2e-8 instead of 0 (``SOAPdistanceNormalized(x, x)``
 
 * ``d**2`` (equivalently the kernel value ``k``) agrees to ``atol`` ABSOLUTE: 1e-12 for the fp64 path;
   for float32 DATA what the kernels achieve against the fp64 oracle on the same (float32-rounded) inputs,
-  not merely the 1e-6 of BASELINE.json's north_star: 2e-7 for the time-lag kernels (measured 4.2e-8,
-  ``profiles/r01_accuracy.txt``); 1e-6 for the pair kernels (int8 x 3 digits = 24 bits of the largest element
+  not merely the 1e-6 of BASELINE.json's north_star: 4e-7 for the time-lag kernels (fp32 products summed in 8-term
+  fp32 chains: measured 4.2e-8 on benchmark-sized rows, ``profiles/r02_accuracy.txt``; up to 2.5e-7 on the very
+  short rows of the fuzz tests over 12 extra seeds, ``scripts/fuzz_soak.sh`` -- 2e-7 held for the pinned seeds only); 1e-6 for the pair kernels (int8 x 3 digits = 24 bits of the largest element
   of a row: measured 2.2e-7 on normalised SOAP vectors, 5.5e-7 on short unnormalised random ones) and where the
   expected values are the REFERENCE's own float32 arithmetic (``f32_ref``: numpy's float32 dot is itself 1.4e-6
   away from the exact value);
 * ``d`` agrees RELATIVE to 1e-12 (fp64) / 1e-6 (float32 data) wherever ``d >= d_rel_min``: 0.1 for fp64,
-  0.25 for the float32 time-lag path and 0.5 for the float32 pair path (rel err of d = err(k) / (2 d^2));
+  0.5 for the float32 paths (rel err of d = err(d^2) / (2 d^2): an absolute 4e-7 on d^2 is a relative 1e-6 on d only from
+  d = 0.45 upwards);
 * NaNs: a NaN on either side is accepted only against NaN or against ``d**2 <= atol`` on the
   other side (both are "k rounded to just above / just below 1").
 """
 import numpy as np
 
 #: absolute tolerance on d**2 per path
-TOL2 = {"f64": 1e-12, "f32": 1e-6, "f32_timelag": 2e-7, "f32_ref": 1e-6}
+TOL2 = {"f64": 1e-12, "f32": 1e-6, "f32_timelag": 4e-7, "f32_ref": 1e-6}
 #: relative tolerance on d (where d >= D_REL_MIN)
 TOL = {"f64": 1e-12, "f32": 1e-6, "f32_timelag": 1e-6, "f32_ref": 1e-6}
-D_REL_MIN = {"f64": 0.1, "f32": 0.5, "f32_timelag": 0.25, "f32_ref": 0.5}
+D_REL_MIN = {"f64": 0.1, "f32": 0.5, "f32_timelag": 0.5, "f32_ref": 0.5}
 
 
 def assert_distance_parity(got, want, path="f64", d_rel_min=None, what=""):

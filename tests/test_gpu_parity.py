@@ -28,6 +28,13 @@ def S():
     return cpctools_b200
 
 
+def _fuzz_offset():
+    """SOAP_FUZZ_SEED=n shifts the seeds of the fuzz tests (soak runs: scripts/fuzz_soak.sh); default 0 = the pinned cases."""
+    import os
+
+    return int(os.environ.get("SOAP_FUZZ_SEED", "0"))
+
+
 def _kinds(S):
     return {
         "simple": (S.simpleSOAPdistance, O.KIND_SIMPLE, 1),
@@ -1028,7 +1035,7 @@ def test_fuzz_random_shapes_against_oracle(S):
     """40 seeded random cases over odd/even dimensions, tiny and ragged frame / atom counts, one to
     four windows, both dtypes, with and without expansion: the time-lag kernel (both staging paths),
     the expansion kernel and the SIMT pair kernel against the oracle."""
-    rng = np.random.default_rng(20261020)
+    rng = np.random.default_rng(20261020 + _fuzz_offset())
     for case in range(40):
         nmax, lmax = int(rng.integers(1, 7)), int(rng.integers(0, 6))
         ns = int(rng.integers(1, 4))
@@ -1075,7 +1082,7 @@ def test_fuzz_tensor_core_pairs_and_row_minima(S):
     from cpctools_b200 import _lib
     from cpctools_b200.classify import pairs_device
 
-    rng = np.random.default_rng(77)
+    rng = np.random.default_rng(77 + _fuzz_offset())
     names = ["normalized", "simple", "kernel2"]
     for case in range(16):
         M, K, D = int(rng.integers(128, 900)), int(rng.integers(256, 1500)), int(rng.integers(32, 700))
@@ -1124,7 +1131,7 @@ def test_fuzz_timelag_raw_dimensions_and_kinds(S):
     from cpctools_b200 import _lib
     from cpctools_b200.analysis import timelag_device
 
-    rng = np.random.default_rng(4242)
+    rng = np.random.default_rng(4242 + _fuzz_offset())
     kinds = [("simple", _lib.KIND_SIMPLE, O.KIND_SIMPLE, 1), ("kernel1", _lib.KIND_KERNEL, O.KIND_KERNEL, 1),
              ("kernel2", _lib.KIND_KERNEL, O.KIND_KERNEL, 2), ("normalized", _lib.KIND_NORMALIZED, O.KIND_NORMALIZED, 1)]
     for case in range(30):
