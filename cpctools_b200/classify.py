@@ -296,9 +296,23 @@ def _fused_blocks(SOAPTrajData, setup, kind, power, doNormalize, want_dist, fram
         dist = th.empty((n, K), dtype=th.float64, device="cuda") if want_dist else None
         amin = th.empty(n, dtype=th.float64, device="cuda")
         arg = th.empty(n, dtype=th.int32, device="cuda")
+        refw, mult, D = setup["refw"], setup["mult"], Dc
+        unit = 16 // rows.element_size()
+        if Dc % unit and n >= 4096:
+            # soap_classify's tiled (TMA) kernel wants rows that are whole 16-byte units; its warp-per-vector
+            # fallback is 5-10x slower (profiles/r02_classify_unaligned.txt).  One padding pass on the device --
+            # zero columns, zero reference weights -- costs two extra passes over the rows and is still 2-4x faster.
+            D = (Dc + unit - 1) // unit * unit
+            padded = th.zeros((n, D), dtype=rows.dtype, device=rows.device)
+            padded[:, :Dc] = rows
+            rows = padded
+            if "refw_pad" not in setup:
+                setup["refw_pad"] = th.nn.functional.pad(refw, (0, D - Dc)).contiguous()
+                setup["mult_pad"] = None if mult is None else th.nn.functional.pad(mult, (0, D - Dc)).contiguous()
+            refw, mult = setup["refw_pad"], setup["mult_pad"]
         rc = lib.soap_classify(
-            rows.data_ptr(), None if setup["mult"] is None else setup["mult"].data_ptr(), setup["refw"].data_ptr(),
-            setup["norm2"].data_ptr(), n, Dc, K, kind, int(power), 1 if doNormalize else 0, _device.dtype_code(rows),
+            rows.data_ptr(), None if mult is None else mult.data_ptr(), refw.data_ptr(),
+            setup["norm2"].data_ptr(), n, D, K, kind, int(power), 1 if doNormalize else 0, _device.dtype_code(rows),
             None if dist is None else dist.data_ptr(), arg.data_ptr(), amin.data_ptr(), _device.stream_ptr(),
         )
         _lib.check(rc, "soap_classify")

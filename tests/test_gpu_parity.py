@@ -699,6 +699,34 @@ def test_classification_shapes_vs_oracle(S, nmax, lmax, K):
     assert_array_equal(cl.distances, np.amin(got, axis=-1))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_classification_pads_unaligned_rows_for_the_tiled_kernel(S, dtype):
+    """Rows that are not whole 16-byte units (mono-species n = l = 6: Dc 147) would take soap_classify's slow
+    warp-per-vector kernel; from 4096 vectors per block upwards the host pads them once and runs the tiled kernel.
+    Both routes against the oracle, and the same arg-minima from both."""
+    from cpctools_b200 import classify as C
+
+    lmax = nmax = 6
+    dc, K = (lmax + 1) * nmax * (nmax + 1) // 2, 7
+    assert (dc * np.dtype(dtype).itemsize) % 16 != 0
+    raw = synthetic_soap((40, 128, dc), seed=3, kind="W", dtype=dtype)       # 5120 vectors in one block
+    attrs = {"l_max": lmax, "n_max": nmax, "species": ["Au"], "species_location_Au-Au": [0, dc]}
+    rng = np.random.default_rng(9)
+    spectra = O.normalizeArray(rng.random((K, (lmax + 1) * nmax * nmax)))
+    refs = S.SOAPReferences([f"r{k}" for k in range(K)], spectra, lmax, nmax)
+    orefs = type("R", (), {"names": refs.names, "spectra": spectra, "lmax": lmax, "nmax": nmax, "__len__": lambda self: K})()
+    ds = FakeSOAPDataset(raw, 40, attrs)                                     # one chunk -> padded route
+    small = FakeSOAPDataset(raw, 8, attrs)                                   # 1024 vectors per block -> fallback kernel
+    want = O.getDistancesFromRefNormalized(FakeSOAPDataset(raw.astype(np.float64), 40, attrs), orefs)
+    path = "f64" if dtype == np.float64 else "f32"
+    got_pad = S.getDistancesFromRefNormalized(ds, refs)
+    got_fb = S.getDistancesFromRefNormalized(small, refs)
+    assert_distance_parity(got_pad, want, path, what="padded rows, tiled kernel")
+    assert_distance_parity(got_fb, want, path, what="warp-per-vector kernel")
+    a, b = S.applyClassification(ds, refs, S.SOAPdistanceNormalized, doNormalize=True), S.applyClassification(small, refs, S.SOAPdistanceNormalized, doNormalize=True)
+    assert (a.references == b.references).mean() > 0.999  # (a near-tie may flip between two summation orders)
+
+
 def test_argmin_numpy_rules(S):
     """ties -> first index; NaN -> first NaN (numpy.argmin / amin, classify.py:274-275)."""
     import torch
