@@ -31,6 +31,7 @@ namespace soapb {
 
 constexpr int kBlk = 32;     // frames per block == lanes per warp
 constexpr int kTlWarps = 8;  // consumer warps (two per SM sub-partition)
+constexpr int kPairDefault = -1;  // SOAP_TL_PAIR default (timelag_pair.cuh): -1 = float32 data only (measured)
 
 struct TimelagPlan {
   int unit_elems, n_units, split, upp, stride, R, ahead, Q, max_lag, cw, mbuf;
@@ -590,6 +591,7 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace soapb
 #include "timelag_rb.cuh"
+#include "timelag_pair.cuh"
 namespace soapb {
 
 // The register-blocked kernel is OPT-IN (SOAP_TL_RB=1): on B200 it is slower than timelag_kernel (0.43 against
@@ -781,6 +783,74 @@ static int launch_timelag(const void *X, const void *mult, double *scratch, int6
   return check_launch("timelag_kernel");
 }
 
+// ---- two frames per lane (timelag_pair.cuh) --------------------------------------------------------------------------
+struct PairChoice {
+  bool use;
+  int w[4], perm[4];  // w[k] = windows[perm[k]], window 1 first
+};
+static PairChoice pair_choose(int64_t F, int nw, const int *windows, int kind, int bulk_ok, int es) {
+  PairChoice ch;
+  memset(&ch, 0, sizeof(ch));
+  // SOAP_TL_PAIR: 1 = use it whenever it applies, 0 = never.  Default: float32 data only -- interleaved A/B on
+  // 1000 x 4096 x 1224, windows 1,5,10,50 (profiles/r02_timelag_pair_ab.txt): fp32 4.01 / 4.26 / 4.38 ms against
+  // 4.23 / 4.47 / 4.66 (5-6 % faster, every round), fp64 8.90-8.96 against 8.79-8.97 (no gain: at 162-168 registers
+  // the fp64 variant cannot keep two units of loads in flight; the microbenchmark of the bare loops promised 12 %)
+  const int mode = env_int("SOAP_TL_PAIR", kPairDefault);
+  const bool on = mode == 1 || (mode < 0 && es == 4 && env_int("SOAP_TL_RB", -1) != 1);  // (an explicit SOAP_TL_RB=1 wins)
+  if (!on || bulk_ok != 1 || (F & 1) || nw < 3 || nw > 4 || kind == SOAP_KIND_EUCLID || kind == SOAP_KIND_EUCLID_NORMALIZED) return ch;
+  int one = -1;
+  for (int k = 0; k < nw; ++k) {
+    if (windows[k] > kPrBlk) return ch;
+    if (windows[k] == 1) one = k;
+  }
+  if (one < 0) return ch;
+  int n = 0;
+  ch.perm[n++] = one;
+  for (int k = 0; k < nw; ++k)
+    if (k != one) ch.perm[n++] = k;
+  for (int k = 0; k < nw; ++k) ch.w[k] = windows[ch.perm[k]];
+  ch.use = true;
+  return ch;
+}
+
+template <typename T, int NW, bool HM>
+static int launch_timelag_pair(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D, const PairPlan &pl,
+                               const PairChoice &ch, cudaStream_t s) {
+  auto kern = timelag_pair_kernel<T, NW, HM, true, 2>;
+  if constexpr (NW == 4 && HM) {  // load-batch experiments (scripts/tl_sweep.py): fp32 1 / 2 / 3 units = 4.90 / 4.14 / 4.74 ms
+    const int ub = env_int("SOAP_TL_PAIR_UB", 2);
+    if (ub == 1) kern = timelag_pair_kernel<T, NW, HM, true, 1>;
+    if (ub == 3) kern = timelag_pair_kernel<T, NW, HM, true, 3>;
+  }
+  SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  const int threads = (kPrWarps + 2) * 32;
+  int per_sm = 0;
+  SOAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, pl.smem));
+  SOAP_REQUIRE(per_sm >= 1, "soap_timelag: the pair kernel does not fit on an SM (%zu bytes of shared memory)", pl.smem);
+  long long grid = (long long)persistent_sms() * per_sm;
+  if (grid < 1) grid = 1;
+  const int force_grid = env_int("SOAP_TL_GRID", 0);
+  if (force_grid > 0) grid = force_grid;
+  const bool atom_major = tl_atom_major(A);
+  const long long n_items = (long long)A * pl.split;
+  if (grid > (atom_major ? (long long)A : n_items)) grid = atom_major ? (long long)A : n_items;
+  SOAP_REQUIRE(!atom_major || grid <= tl_max_grid(), "soap_timelag: grid %lld exceeds the accumulator area", grid);
+  const int64_t nblk = (F + kPrBlk - 1) / kPrBlk;
+  SOAP_REQUIRE((n_items + grid - 1) / grid * nblk + (long long)pl.split * nblk < 2147483647LL, "soap_timelag: too many blocks per CTA");
+  double *cta_acc = atom_major ? scratch + (size_t)A * pl.Q * (size_t)F : nullptr;
+  const int64_t row_words = (int64_t)A * D * (int64_t)sizeof(T) / 8;
+  SOAP_REQUIRE(row_words < 2147483647LL, "soap_timelag: a frame of %lld bytes exceeds the tensor-map coordinate range", (long long)row_words * 8);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  int rc = make_tensor_map_pairs(&tmap, X, F / 2, row_words, pl.stride / 8);
+  if (rc) return rc;
+  const int4 win4 = make_int4(ch.w[0], ch.w[1], ch.w[2], NW > 3 ? ch.w[3] : 0);
+  ProfScope prof(SOAP_PROF_TIMELAG, s);
+  kern<<<(unsigned)grid, threads, pl.smem, s>>>(static_cast<const T *>(mult), scratch, cta_acc, (long long)F, (long long)A, D, pl.split, pl.upp,
+                                                pl.stride, pl.mbuf, win4, tmap);
+  return check_launch("timelag_pair_kernel");
+}
+
 template <int NW>
 static int launch_finalize(const double *scratch, double *t, const int64_t *off, int64_t F, int64_t A,
                            int split, const int *w, int kind, int power, cudaStream_t s) {
@@ -827,11 +897,16 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
   const int plan_dim = ((size_t)dim * es) % 16 != 0 ? dim + 16 / es - 1 : dim;  // shifted rows: the widest window
   if (!make_plan(n_frames, plan_dim, es, windows_host, n_windows, pl))
     return rb_bytes + tl_pad_bytes(dim, es) + tl_inv_bytes(n_frames, n_atoms);
-  // totals sums[a][q][f] + one accumulator [q][frames padded to 32] per resident CTA
-  const size_t padded = (size_t)((n_frames + kBlk - 1) / kBlk) * kBlk;
+  int pair_split = 0;  // the pair kernel cuts rows into more pieces (timelag_pair.cuh)
+  {
+    PairPlan pp;
+    if (pr_make_plan(n_frames, plan_dim, es, n_windows, pp)) pair_split = pp.split;
+  }
+  // totals sums[a][q][f] + one accumulator [q][frames padded to a block: 32, or 64 for the pair kernel] per resident CTA
+  const size_t padded = (size_t)((n_frames + kPrBlk - 1) / kPrBlk) * kPrBlk;
   size_t bytes = tl_atom_major(n_atoms)
                      ? ((size_t)n_atoms * pl.Q * (size_t)n_frames + (size_t)tl_max_grid() * pl.Q * padded) * sizeof(double)
-                     : (size_t)n_atoms * pl.split * pl.Q * (size_t)n_frames * sizeof(double);
+                     : (size_t)n_atoms * (size_t)(pl.split > pair_split ? pl.split : pair_split) * pl.Q * (size_t)n_frames * sizeof(double);
   return (bytes > rb_bytes ? bytes : rb_bytes) + tl_pad_bytes(dim, es) + tl_inv_bytes(n_frames, n_atoms);
 }
 
@@ -886,6 +961,27 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
     if (rc) return rc;
     mult = table;
     bulk_ok |= 32;
+  }
+  {
+    const PairChoice pc = pair_choose(n_frames, n_windows, windows_host, kind, bulk_ok, es);
+    PairPlan pp;
+    if (pc.use && pr_make_plan(n_frames, dim, es, n_windows, pp)) {
+#define PR_CASE(T, NW)                                                                                                      \
+  rc = mult ? launch_timelag_pair<T, NW, true>(X, mult, sc, n_frames, n_atoms, dim, pp, pc, s)                              \
+            : launch_timelag_pair<T, NW, false>(X, mult, sc, n_frames, n_atoms, dim, pp, pc, s)
+      if (dtype == SOAP_F64) {
+        if (n_windows == 3) PR_CASE(double, 3); else PR_CASE(double, 4);
+      } else {
+        if (n_windows == 3) PR_CASE(float, 3); else PR_CASE(float, 4);
+      }
+#undef PR_CASE
+      if (rc) return rc;
+      int64_t off[4] = {0, 0, 0, 0};
+      for (int k = 0; k < n_windows; ++k) off[k] = t_offsets_host[pc.perm[k]];
+      const int fsplit = tl_atom_major(n_atoms) ? 1 : pp.split;
+      if (n_windows == 3) return launch_finalize<3>(sc, t, off, n_frames, n_atoms, fsplit, pc.w, kind, power, s);
+      return launch_finalize<4>(sc, t, off, n_frames, n_atoms, fsplit, pc.w, kind, power, s);
+    }
   }
   {
     const RbChoice ch = rb_choose(n_frames, n_atoms, dim, es, windows_host, n_windows, kind, bulk_ok != 0);

@@ -389,6 +389,57 @@ def test_timelag_register_blocked_kernel(S, F, A, D, dtype, windows, monkeypatch
         assert_distance_parity(np.delete(got, 1, axis=1), np.delete(weighted[0], 1, axis=1), path, what="NaN neighbour")
 
 
+@pytest.mark.parametrize(
+    "F,A,D,dtype,windows",
+    [
+        (200, 40, 1224, np.float64, (1, 5, 10, 50)),   # the bench's row: ten pieces, (atom, piece) items dealt round robin
+        (130, 700, 324, np.float64, (1, 5, 10, 50)),   # atom-major mode (pieces summed on chip), a ragged last block
+        (66, 9, 1224, np.float32, (5, 1, 64)),         # window 1 not first, the longest window the ring keeps, 3 windows
+        (64, 3, 8, np.float64, (1, 2, 3, 4)),          # one block, rows of four units, even and odd lags side by side
+        (2, 5, 40, np.float32, (1, 1, 1)),             # the smallest trajectory
+        (400, 300, 36, np.float32, (1, 7, 32, 33)),    # short rows, many items per CTA
+        (1000, 64, 1728, np.float64, (1, 5, 10, 50)),  # materialised vectors without multiplicities path too
+    ],
+)
+def test_timelag_two_frames_per_lane_kernel(S, F, A, D, dtype, windows, monkeypatch):
+    """The sweep kernel with a frame PAIR per lane (timelag_pair.cuh: even / odd ring halves through a 3-D tensor map,
+    lag-1 partner of the odd frame from registers, 64-frame blocks) forced on: against the oracle, against the
+    lane-per-frame kernel, and bitwise reproducible across grid sizes."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.analysis import timelag_device
+
+    rng = np.random.default_rng(F * 1000 + A + D)
+    X = rng.random((F, A, D)).astype(dtype)
+    m = (1.0 + (rng.random(D) < 0.4)).astype(dtype)
+    path = "f64" if dtype == np.float64 else "f32_timelag"
+    Xd, md = torch.from_numpy(X).cuda(), torch.from_numpy(m).cuda()
+    monkeypatch.setenv("SOAP_TL_PAIR", "1")
+    plain = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1)]
+    weighted = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    monkeypatch.setenv("SOAP_TL_GRID", "3")
+    weighted3 = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    monkeypatch.delenv("SOAP_TL_GRID")
+    monkeypatch.setenv("SOAP_TL_PAIR", "0")
+    old = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    X64 = X.astype(np.float64)
+    Xw = X64 * np.sqrt(m.astype(np.float64))
+    for k, w in enumerate(windows):
+        assert plain[k].shape == (F - w, A)
+        assert_distance_parity(plain[k], O.timeSOAP_batched(X64, window=w, kind=O.KIND_SIMPLE)[0], path, what=f"plain w{w}")
+        assert_distance_parity(weighted[k], O.timeSOAP_batched(Xw, window=w, kind=O.KIND_SIMPLE)[0], path, what=f"weighted w{w}")
+        assert_distance_parity(weighted[k], old[k], path, what=f"vs lane-per-frame kernel w{w}")
+        assert_array_equal(weighted[k], weighted3[k])
+    if A >= 3:  # an atom full of NaN poisons only itself
+        Xn = X.copy()
+        Xn[:, 1, :] = np.nan
+        monkeypatch.setenv("SOAP_TL_PAIR", "1")
+        got = [t.cpu().numpy() for t in timelag_device(torch.from_numpy(Xn).cuda(), windows, _lib.KIND_SIMPLE, 1, mult=md)]
+        for k in range(len(windows)):
+            assert np.isnan(got[k][:, 1]).all()
+            assert_array_equal(np.delete(got[k], 1, axis=1), np.delete(weighted[k], 1, axis=1))
+
+
 @pytest.mark.parametrize("D,dtype", [(1198, np.float32), (1197, np.float32), (147, np.float32), (7, np.float32), (1197, np.float64)])
 def test_timelag_rows_ending_in_half_a_unit_do_not_leak_the_next_row(S, D, dtype):
     """Rows that are not whole 16-byte units (raw quippy fp32: 1198 floats; dscribe 3 species n = l = 6: 1197) go
