@@ -78,8 +78,9 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
 }
 
 // U units of a frame pair against the NW lagged frames of each.  acc[0 .. 2Q) belong to the even frame, acc[2Q .. 4Q)
-// to the odd one (two chains per sum, as in accum_units_f64).  W1: the first window is 1 -- the odd frame's partner
-// is the even frame itself and ye[0] addresses frame 2p - 1.
+// to the odd one (slots 2q and 2q + 1 of a sum: the float32 variant keeps two chains per sum, the float64 one uses the
+// first only).  W1: the first window is 1 -- the odd frame's partner is the even frame itself and ye[0] addresses
+// frame 2p - 1.
 template <int NW, int U, bool HM, bool W1>
 __device__ __forceinline__ void accum_pair_f64(uint32_t m_addr, uint32_t xe, uint32_t xo, const uint32_t (&ye)[NW], const uint32_t (&yo)[NW],
                                                uint32_t off, uint32_t ustep, double (&acc)[4 * (NW + 1)]) {
@@ -97,20 +98,18 @@ __device__ __forceinline__ void accum_pair_f64(uint32_t m_addr, uint32_t xe, uin
       if (!(W1 && k == 0)) po[k][j] = lds_d2(yo[k] + o);
     }
   }
+  // ONE chain per sum (timelag_kernel keeps two): 10 sums x 2 frames are already 20 independent chains, and the
+  // 20 registers saved are what lets two units of loads stay in flight under the 168-register cap
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const double am0 = a[j].x * m[j].x, am1 = a[j].y * m[j].y, bm0 = b[j].x * m[j].x, bm1 = b[j].y * m[j].y;
-    acc[0] = fma(am0, a[j].x, acc[0]);
-    acc[1] = fma(am1, a[j].y, acc[1]);
-    acc[Q2] = fma(bm0, b[j].x, acc[Q2]);
-    acc[Q2 + 1] = fma(bm1, b[j].y, acc[Q2 + 1]);
+    acc[0] = fma(am1, a[j].y, fma(am0, a[j].x, acc[0]));
+    acc[Q2] = fma(bm1, b[j].y, fma(bm0, b[j].x, acc[Q2]));
 #pragma unroll
     for (int k = 0; k < NW; ++k) {
-      acc[2 * k + 2] = fma(am0, pe[k][j].x, acc[2 * k + 2]);
-      acc[2 * k + 3] = fma(am1, pe[k][j].y, acc[2 * k + 3]);
+      acc[2 * k + 2] = fma(am1, pe[k][j].y, fma(am0, pe[k][j].x, acc[2 * k + 2]));
       const double2 q = (W1 && k == 0) ? a[j] : po[k][j];
-      acc[Q2 + 2 * k + 2] = fma(bm0, q.x, acc[Q2 + 2 * k + 2]);
-      acc[Q2 + 2 * k + 3] = fma(bm1, q.y, acc[Q2 + 2 * k + 3]);
+      acc[Q2 + 2 * k + 2] = fma(bm1, q.y, fma(bm0, q.x, acc[Q2 + 2 * k + 2]));
     }
   }
 }
