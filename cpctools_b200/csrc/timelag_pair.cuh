@@ -85,7 +85,11 @@ template <int NW, int U, bool HM, bool W1>
 __device__ __forceinline__ void accum_pair_f64(uint32_t m_addr, uint32_t xe, uint32_t xo, const uint32_t (&ye)[NW], const uint32_t (&yo)[NW],
                                                uint32_t off, uint32_t ustep, double (&acc)[4 * (NW + 1)]) {
   constexpr int Q2 = 2 * (NW + 1);
-  double2 m[U], a[U], b[U], pe[NW][U], po[NW][U];
+  // Two phases, so that at most 3 + NW loads per unit are live at once (the kernel sits at the 168-register cap of a
+  // 10-warp CTA): first the even frame against its partners (and everything the odd frame needs from registers),
+  // then the odd frame's partners.  ONE chain per sum (timelag_kernel keeps two): (NW + 1) sums x 2 frames are
+  // already independent chains.
+  double2 m[U], a[U], b[U], pe[NW][U];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const uint32_t o = off + j * ustep;
@@ -93,24 +97,26 @@ __device__ __forceinline__ void accum_pair_f64(uint32_t m_addr, uint32_t xe, uin
     a[j] = lds_d2(xe + o);
     b[j] = lds_d2(xo + o);
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      pe[k][j] = lds_d2(ye[k] + o);
-      if (!(W1 && k == 0)) po[k][j] = lds_d2(yo[k] + o);
-    }
+    for (int k = 0; k < NW; ++k) pe[k][j] = lds_d2(ye[k] + o);
   }
-  // ONE chain per sum (timelag_kernel keeps two): 10 sums x 2 frames are already 20 independent chains, and the
-  // 20 registers saved are what lets two units of loads stay in flight under the 168-register cap
+  double2 bm[U];
 #pragma unroll
   for (int j = 0; j < U; ++j) {
-    const double am0 = a[j].x * m[j].x, am1 = a[j].y * m[j].y, bm0 = b[j].x * m[j].x, bm1 = b[j].y * m[j].y;
+    const double am0 = a[j].x * m[j].x, am1 = a[j].y * m[j].y;
+    bm[j] = make_double2(b[j].x * m[j].x, b[j].y * m[j].y);
     acc[0] = fma(am1, a[j].y, fma(am0, a[j].x, acc[0]));
-    acc[Q2] = fma(bm1, b[j].y, fma(bm0, b[j].x, acc[Q2]));
+    acc[Q2] = fma(bm[j].y, b[j].y, fma(bm[j].x, b[j].x, acc[Q2]));
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      acc[2 * k + 2] = fma(am1, pe[k][j].y, fma(am0, pe[k][j].x, acc[2 * k + 2]));
-      const double2 q = (W1 && k == 0) ? a[j] : po[k][j];
-      acc[Q2 + 2 * k + 2] = fma(bm1, q.y, fma(bm0, q.x, acc[Q2 + 2 * k + 2]));
-    }
+    for (int k = 0; k < NW; ++k) acc[2 * k + 2] = fma(am1, pe[k][j].y, fma(am0, pe[k][j].x, acc[2 * k + 2]));
+    if (W1) acc[Q2 + 2] = fma(bm[j].y, a[j].y, fma(bm[j].x, a[j].x, acc[Q2 + 2]));
+  }
+#pragma unroll
+  for (int k = W1 ? 1 : 0; k < NW; ++k) {
+    double2 po[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) po[j] = lds_d2(yo[k] + off + j * ustep);
+#pragma unroll
+    for (int j = 0; j < U; ++j) acc[Q2 + 2 * k + 2] = fma(bm[j].y, po[j].y, fma(bm[j].x, po[j].x, acc[Q2 + 2 * k + 2]));
   }
 }
 
