@@ -133,5 +133,9 @@ int main() {
   run<2>(6, 61);
   run<2>(10, 61);
   run<2>(8, 55);
+  run<4>(6, 61);  // 8 warps per CTA in all: 255 registers per thread, room for deeper batches
+  run<6>(6, 61);
+  run<3>(6, 61);
+  run<4>(4, 61);
   return 0;
 }
