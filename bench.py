@@ -317,13 +317,14 @@ def run_gpu_arm(args):
     k_ms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r02_timelag_traffic.json")
+    sweep_kernel = lib.soap_timelag_last_kernel().decode() or "timelag_kernel"
+    tpath = os.path.join(ROOT, "profiles", "r03_timelag_chain_traffic.json" if sweep_kernel == "timelag_chain_kernel" else "r02_timelag_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read+write of one `ncu --set full` capture, scaled by the atom count
         tj = json.load(open(tpath))
         traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * atoms / tj["atoms"] * frames / 1000
         traffic_src = f"{tj['capture']} ({tj['config']}), scaled linearly to this tile"
     roofline = {
-        "bound": "hbm", "kernel": "timelag_kernel<double,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": f"{sweep_kernel}<double, 4 windows>", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": k_ms,
         "kernel_share_of_step": k_ms * len(kernel_ms) / (ev[0].elapsed_time(ev[-1])) if kernel_ms else None,
         "algorithmic_bytes_per_launch": algo_bytes, "scratch_bytes_per_launch": int(scratch_bytes),
@@ -514,7 +515,7 @@ def run_gpu_arm(args):
     ms32 = float(np.mean(_lib.profile_read(_lib.PROF_TIMELAG)))
     _lib.profile_enable(False)
     nb32 = frames * atoms * dc * 4 + sum((frames - w) * atoms * 8 for w in WINDOWS)
-    roofline_f32 = {"bound": "hbm", "kernel": "timelag_kernel<float,4>", "achieved": nb32 / ms32 / 1e6, "peak": peak, "unit": "GB/s",
+    roofline_f32 = {"bound": "hbm", "kernel": f"{lib.soap_timelag_last_kernel().decode()}<float, 4 windows>", "achieved": nb32 / ms32 / 1e6, "peak": peak, "unit": "GB/s",
                     "frac": nb32 / ms32 / 1e6 / peak, "kernel_ms": ms32, "algorithmic_bytes_per_launch": nb32,
                     "pairs_per_s": pairs_per_atom(frames) * atoms / (ms32 * 1e-3), "traffic": None}
     del X32

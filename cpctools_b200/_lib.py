@@ -39,6 +39,7 @@ SIGNATURES = {
     "soap_profile_read": (c_int, [c_int, POINTER(ctypes.c_float), c_int]),
     "soap_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "soap_expand_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "soap_timelag_last_kernel": (c_char_p, []),
     "soap_timelag_scratch_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, POINTER(c_int), c_int]),
     "soap_timelag": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), c_int64, c_int64, c_int,
                              POINTER(c_int), c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -73,6 +74,8 @@ def _needs_rebuild() -> bool:
         os.path.join(CSRC, "common.cuh"),
         os.path.join(CSRC, "tc05.cuh"),
         os.path.join(CSRC, "timelag_rb.cuh"),
+        os.path.join(CSRC, "timelag_pair.cuh"),
+        os.path.join(CSRC, "timelag_chain.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "soap_b200.h"),
     ]
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))

@@ -26,11 +26,14 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
+#include <utility>
 
 namespace soapb {
 
 constexpr int kBlk = 32;     // frames per block == lanes per warp
 constexpr int kTlWarps = 8;  // consumer warps (two per SM sub-partition)
+constexpr int kChainDefault = -1;  // SOAP_TL_CHAIN default (timelag_chain.cuh): -1 = float64 data only (measured)
 constexpr int kPairDefault = -1;  // SOAP_TL_PAIR default (timelag_pair.cuh): -1 = float32 data only (measured)
 
 struct TimelagPlan {
@@ -48,6 +51,8 @@ static long long tl_max_grid() { return (long long)num_sms() * 4; }
 // a CTA owns whole atoms (and sums their pieces on chip) when there are enough atoms to keep every SM busy
 // with little imbalance; with fewer atoms the (atom, piece) items are dealt round robin
 static bool tl_atom_major(int64_t n_atoms) { return n_atoms >= 4ll * num_sms(); }
+
+static const char *g_tl_last_kernel = "";
 
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
@@ -592,6 +597,7 @@ __global__ void __launch_bounds__(256)
 }  // namespace soapb
 #include "timelag_rb.cuh"
 #include "timelag_pair.cuh"
+#include "timelag_chain.cuh"
 namespace soapb {
 
 // The register-blocked kernel is OPT-IN (SOAP_TL_RB=1): on B200 it is slower than timelag_kernel (0.43 against
@@ -667,6 +673,7 @@ static int launch_timelag_rb(const void *X, const void *mult, double *scratch, i
   ProfScope prof(SOAP_PROF_TIMELAG, s);
   kern<<<(unsigned)grid, kRbThreads, pl.smem, s>>>(table, scratch, cta_acc, (long long)F, (long long)A, pl.n_units, pl.c,
                                                    pl.pieces, (int)pl.mult_elems, win4, ch.hist, env_int("SOAP_RB_DIAG", 0), pl.st, tm[0], tm[1], tm[2], tm[3]);
+  g_tl_last_kernel = "timelag_rb_kernel";
   return check_launch("timelag_rb_kernel");
 }
 
@@ -780,6 +787,7 @@ static int launch_timelag(const void *X, const void *mult, double *scratch, int6
   kern<<<(unsigned)grid, threads, pl.smem, s>>>(static_cast<const T *>(X), static_cast<const T *>(mult), scratch, cta_acc,
                                                 inv_norm, (long long)F, (long long)A, D, pl.split, pl.upp, pl.stride, pl.R,
                                                 (pl.max_lag + kBlk - 1) / kBlk, pl.mbuf, win4, bulk_ok, mult_pitch, tmap);
+  g_tl_last_kernel = "timelag_kernel";
   return check_launch("timelag_kernel");
 }
 
@@ -848,7 +856,103 @@ static int launch_timelag_pair(const void *X, const void *mult, double *scratch,
   ProfScope prof(SOAP_PROF_TIMELAG, s);
   kern<<<(unsigned)grid, threads, pl.smem, s>>>(static_cast<const T *>(mult), scratch, cta_acc, (long long)F, (long long)A, D, pl.split, pl.upp,
                                                 pl.stride, pl.mbuf, win4, tmap);
+  g_tl_last_kernel = "timelag_pair_kernel";
   return check_launch("timelag_pair_kernel");
+}
+
+
+// ---- lane = units, lag history in registers (timelag_chain.cuh) ------------------------------------------------------
+// SOAP_TL_CHAIN_U = 3 | 4 units per lane, SOAP_TL_CHAIN_SR = 1 | 0: partial sums through shared memory | by shuffles
+struct ChainChoice {
+  bool use;
+  int nw, ns, w0, c[3];  // ring window (ns = 1) and chain windows c[k] * 5, ascending
+  int w[4], perm[4];     // w[k] = windows[perm[k]] in the kernel's order: ring window first, then the chain windows
+};
+static ChainChoice chain_choose(int64_t F, int64_t A, int nw, const int *windows, int kind, int bulk_ok, int es) {
+  ChainChoice ch;
+  memset(&ch, 0, sizeof(ch));
+  // SOAP_TL_CHAIN: 1 = use it whenever it applies, 0 = never.  Default: float64 data only -- bench.py, 1000 x 12 500 x
+  // 1224 fp64, windows 1,5,10,50 (profiles/r03_bench_chain_ab.txt): 21.8 ms = 0.86 of the HBM peak sustained (0.91
+  // timed alone) against 25.3 ms = 0.74 (0.78) for timelag_kernel; float32 4.5 ms against 4.0 ms for the pair kernel
+  // (1000 x 4096: the fp32 variant issues twice the instructions per byte and five warps cannot hide them)
+  const int mode = env_int("SOAP_TL_CHAIN", kChainDefault);
+  const bool on = mode == 1 || (mode < 0 && es == 8 && env_int("SOAP_TL_RB", -1) != 1 && env_int("SOAP_TL_PAIR", -1) != 1);
+  if (!on || bulk_ok != 1 || nw < 2 || nw > 4 || kind == SOAP_KIND_EUCLID || kind == SOAP_KIND_EUCLID_NORMALIZED) return ch;
+  if (!tl_atom_major(A)) return ch;
+  int ring = -1, nc = 0, ci[3] = {0, 0, 0};
+  for (int k = 0; k < nw; ++k) {
+    const int w = windows[k];
+    if (w % kChS == 0 && w <= kChS * kChH) {
+      if (nc == 3) return ch;
+      ci[nc++] = k;
+    } else {
+      if (ring >= 0 || w > kChB) return ch;
+      ring = k;
+    }
+  }
+  for (int i = 1; i < nc; ++i)
+    for (int j = i; j > 0 && windows[ci[j]] < windows[ci[j - 1]]; --j) {
+      const int t = ci[j];
+      ci[j] = ci[j - 1];
+      ci[j - 1] = t;
+    }
+  for (int i = 1; i < nc; ++i)
+    if (windows[ci[i]] == windows[ci[i - 1]]) return ch;  // (a repeated window takes the general kernel)
+  int n = 0;
+  if (ring >= 0) ch.perm[n++] = ring, ch.ns = 1, ch.w0 = windows[ring];
+  for (int i = 0; i < nc; ++i) ch.perm[n++] = ci[i], ch.c[i] = windows[ci[i]] / kChS;
+  for (int k = 0; k < nw; ++k) ch.w[k] = windows[ch.perm[k]];
+  ch.nw = nw;
+  // instantiated patterns (launch_chain_pattern)
+  const bool p4 = ch.ns == 1 && ch.c[0] == 1 && ch.c[1] == 2 && ch.c[2] == 10;  // (w0, 5, 10, 50)
+  const bool p3 = ch.ns == 1 && ch.c[0] == 1 && ch.c[1] == 2 && ch.c[2] == 0;   // (w0, 5, 10)
+  ch.use = p4 || p3;
+  return ch;
+}
+
+template <typename T, int U, int SR, int NS, int C1, int C2, int C3, bool HM>
+static int launch_timelag_chain(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D, const ChainPlan &pl,
+                                const ChainChoice &ch, cudaStream_t s) {
+  // SR: 0 = shuffle butterfly, 1 = sums through shared memory, 2 + d = the same, loads pipelined d columns ahead
+  auto kern = timelag_chain_kernel<T, U, NS, C1, C2, C3, HM, (SR > 0), (SR >= 2 ? SR - 2 : 0)>;
+  SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  int per_sm = 0;
+  SOAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kChThreads, pl.smem));
+  SOAP_REQUIRE(per_sm >= 1, "soap_timelag: the chain kernel does not fit on an SM (%zu bytes of shared memory)", pl.smem);
+  long long grid = (long long)persistent_sms() * per_sm;
+  if (grid < 1) grid = 1;
+  const int force_grid = env_int("SOAP_TL_GRID", 0);
+  if (force_grid > 0) grid = force_grid;
+  if (grid > (long long)A) grid = (long long)A;
+  SOAP_REQUIRE(grid <= tl_max_grid(), "soap_timelag: grid %lld exceeds the accumulator area", grid);
+  const int64_t nblk = (F + kChB - 1) / kChB;
+  SOAP_REQUIRE(((long long)A * pl.split + grid - 1) / grid * nblk + (long long)pl.split * nblk < 2147483647LL, "soap_timelag: too many blocks per CTA");
+  double *cta_acc = scratch + (size_t)A * pl.Q * (size_t)F;
+  const int64_t row_words = (int64_t)A * D * (int64_t)sizeof(T) / 8;
+  SOAP_REQUIRE(row_words < 2147483647LL, "soap_timelag: a frame of %lld bytes exceeds the tensor-map coordinate range", (long long)row_words * 8);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, pl.pitch / 8, kChB, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE);
+  if (rc) return rc;
+  ProfScope prof(SOAP_PROF_TIMELAG, s);
+  kern<<<(unsigned)grid, kChThreads, pl.smem, s>>>(static_cast<const T *>(mult), scratch, cta_acc, (long long)F, (long long)A, D, pl.split, pl.upp,
+                                                   pl.pitch, (int)pl.blk_bytes, pl.nbuf, ch.w0, tmap);
+  g_tl_last_kernel = "timelag_chain_kernel";
+  return check_launch("timelag_chain_kernel");
+}
+
+template <typename T, int U, int SR>
+static int launch_chain_pattern(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D, const ChainPlan &pl,
+                                const ChainChoice &ch, cudaStream_t s) {
+#define CH_CASE(NS, C1, C2, C3)                                                                                   \
+  if (ch.ns == NS && ch.c[0] == C1 && ch.c[1] == C2 && ch.c[2] == C3)                                             \
+    return mult ? launch_timelag_chain<T, U, SR, NS, C1, C2, C3, true>(X, mult, scratch, F, A, D, pl, ch, s)      \
+                : launch_timelag_chain<T, U, SR, NS, C1, C2, C3, false>(X, mult, scratch, F, A, D, pl, ch, s);
+  CH_CASE(1, 1, 2, 10)
+  CH_CASE(1, 1, 2, 0)
+#undef CH_CASE
+  return set_error(SOAP_EINVAL, "soap_timelag: no chain variant for this window pattern");
 }
 
 template <int NW>
@@ -878,6 +982,8 @@ static int check_windows(int64_t F, const int *w, int nw, const char *who) {
   return SOAP_OK;
 }
 
+extern "C" const char *soap_timelag_last_kernel(void) { return g_tl_last_kernel; }
+
 extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, int dim, int dtype,
                                              const int *windows_host, int n_windows) {
   if (n_frames <= 0 || n_atoms <= 0 || dim <= 0 || !windows_host || n_windows < 1 || n_windows > SOAP_MAX_WINDOWS)
@@ -903,7 +1009,8 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
     if (pr_make_plan(n_frames, plan_dim, es, n_windows, pp)) pair_split = pp.split;
   }
   // totals sums[a][q][f] + one accumulator [q][frames padded to a block: 32, or 64 for the pair kernel] per resident CTA
-  const size_t padded = (size_t)((n_frames + kPrBlk - 1) / kPrBlk) * kPrBlk;
+  // (the chain kernel's 25-frame blocks and up to 5-piece rows fit the same area: F + 24 <= padded + 24)
+  const size_t padded = (size_t)((n_frames + kPrBlk - 1) / kPrBlk) * kPrBlk + kChB;
   size_t bytes = tl_atom_major(n_atoms)
                      ? ((size_t)n_atoms * pl.Q * (size_t)n_frames + (size_t)tl_max_grid() * pl.Q * padded) * sizeof(double)
                      : (size_t)n_atoms * (size_t)(pl.split > pair_split ? pl.split : pair_split) * pl.Q * (size_t)n_frames * sizeof(double);
@@ -961,6 +1068,26 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
     if (rc) return rc;
     mult = table;
     bulk_ok |= 32;
+  }
+  {
+    const ChainChoice cc = chain_choose(n_frames, n_atoms, n_windows, windows_host, kind, bulk_ok, es);
+    ChainPlan cp;
+    const int chU = env_int("SOAP_TL_CHAIN_U", 4);
+    const int chSR = env_int("SOAP_TL_CHAIN_SR", 4);
+    if (cc.use && whole_units && (chU == 3 || chU == 4) && ch_make_plan(dim, es, n_windows, chU, chSR != 0, cp)) {
+#define CH_VAR(UU, SS)                                                                                              \
+  if (chU == UU && chSR == SS)                                                                                      \
+    rc = dtype == SOAP_F64 ? launch_chain_pattern<double, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, s)   \
+                           : launch_chain_pattern<float, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, s);
+      rc = set_error(SOAP_EINVAL, "soap_timelag: no chain variant SOAP_TL_CHAIN_U=%d SOAP_TL_CHAIN_SR=%d", chU, chSR);
+      CH_VAR(4, 0) CH_VAR(4, 1) CH_VAR(4, 3) CH_VAR(4, 4) CH_VAR(4, 5) CH_VAR(3, 4)
+#undef CH_VAR
+      if (rc) return rc;
+      int64_t off[4] = {0, 0, 0, 0};
+      for (int k = 0; k < n_windows; ++k) off[k] = t_offsets_host[cc.perm[k]];
+      if (n_windows == 3) return launch_finalize<3>(sc, t, off, n_frames, n_atoms, 1, cc.w, kind, power, s);
+      return launch_finalize<4>(sc, t, off, n_frames, n_atoms, 1, cc.w, kind, power, s);
+    }
   }
   {
     const PairChoice pc = pair_choose(n_frames, n_windows, windows_host, kind, bulk_ok, es);

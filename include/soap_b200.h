@@ -99,6 +99,10 @@ int soap_expand_normalize(const void *in, void *out, const int32_t *idx, int64_t
 #define SOAP_MAX_WINDOWS 4
 size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, int dim, int dtype,
                                   const int *windows_host, int n_windows);
+/* name of the sweep kernel the last soap_timelag call of this process launched (bench.py's roofline names it):
+ * "timelag_kernel" (lane = frame), "timelag_pair_kernel" (two frames per lane), "timelag_chain_kernel" (lane =
+ * units, lag history in registers), "timelag_rb_kernel"; "" before the first call */
+const char *soap_timelag_last_kernel(void);
 int soap_timelag(const void *X, const void *mult, double *t, const int64_t *t_offsets_host,
                  int64_t n_frames, int64_t n_atoms, int dim, const int *windows_host,
                  int n_windows, int kind, int power, int dtype, void *scratch, void *stream);

@@ -440,6 +440,57 @@ def test_timelag_two_frames_per_lane_kernel(S, F, A, D, dtype, windows, monkeypa
             assert_array_equal(np.delete(got[k], 1, axis=1), np.delete(weighted[k], 1, axis=1))
 
 
+@pytest.mark.parametrize(
+    "F,A,D,dtype,windows",
+    [
+        (130, 600, 1224, np.float64, (1, 5, 10, 50)),   # the headline sweep: five pieces per row, the last one ragged
+        (60, 700, 36, np.float64, (3, 5, 10)),          # three windows, ring window 3, an odd number of blocks per item
+        (77, 640, 200, np.float32, (50, 1, 10, 5)),     # one piece of 50 units, windows in any order
+        (26, 600, 1728, np.float32, (2, 10, 5)),        # two blocks, the second nearly empty; four pieces
+        (120, 592, 516, np.float64, (25, 5, 10, 50)),   # the largest ring window; two full columns + a ragged one
+    ],
+)
+def test_timelag_chain_kernel(S, F, A, D, dtype, windows, monkeypatch):
+    """The sweep kernel with lane = units and the lag history in registers (timelag_chain.cuh: warp = frame mod 5,
+    windows 5 / 10 / 50 from registers, transposing butterfly over the lanes) forced on: against the oracle, against
+    the lane-per-frame kernel, bitwise reproducible across grid sizes, NaN isolation."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.analysis import timelag_device
+
+    rng = np.random.default_rng(F * 1000 + A + D)
+    X = rng.random((F, A, D)).astype(dtype)
+    m = (1.0 + (rng.random(D) < 0.4)).astype(dtype)
+    path = "f64" if dtype == np.float64 else "f32_timelag"
+    Xd, md = torch.from_numpy(X).cuda(), torch.from_numpy(m).cuda()
+    monkeypatch.setenv("SOAP_TL_CHAIN", "1")
+    _lib.profile_enable(True)
+    plain = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1)]
+    weighted = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    monkeypatch.setenv("SOAP_TL_GRID", "3")
+    weighted3 = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    monkeypatch.delenv("SOAP_TL_GRID")
+    monkeypatch.setenv("SOAP_TL_CHAIN", "0")
+    old = [t.cpu().numpy() for t in timelag_device(Xd, windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    _lib.profile_enable(False)
+    X64 = X.astype(np.float64)
+    Xw = X64 * np.sqrt(m.astype(np.float64))
+    for k, w in enumerate(windows):
+        assert plain[k].shape == (F - w, A)
+        assert_distance_parity(plain[k], O.timeSOAP_batched(X64, window=w, kind=O.KIND_SIMPLE)[0], path, what=f"plain w{w}")
+        assert_distance_parity(weighted[k], O.timeSOAP_batched(Xw, window=w, kind=O.KIND_SIMPLE)[0], path, what=f"weighted w{w}")
+        assert_distance_parity(weighted[k], old[k], path, what=f"vs lane-per-frame kernel w{w}")
+        assert_array_equal(weighted[k], weighted3[k])
+    # an atom full of NaN poisons only itself
+    Xn = X.copy()
+    Xn[:, 1, :] = np.nan
+    monkeypatch.setenv("SOAP_TL_CHAIN", "1")
+    got = [t.cpu().numpy() for t in timelag_device(torch.from_numpy(Xn).cuda(), windows, _lib.KIND_SIMPLE, 1, mult=md)]
+    for k in range(len(windows)):
+        assert np.isnan(got[k][:, 1]).all()
+        assert_array_equal(np.delete(got[k], 1, axis=1), np.delete(weighted[k], 1, axis=1))
+
+
 @pytest.mark.parametrize("D,dtype", [(1198, np.float32), (1197, np.float32), (147, np.float32), (7, np.float32), (1197, np.float64)])
 def test_timelag_rows_ending_in_half_a_unit_do_not_leak_the_next_row(S, D, dtype):
     """Rows that are not whole 16-byte units (raw quippy fp32: 1198 floats; dscribe 3 species n = l = 6: 1197) go
