@@ -452,7 +452,14 @@ def run_gpu_arm(args):
         dist.all_gather_into_tensor(samples, mine)
         nb = (rank + 1) % world
         per = total_atoms // world
+        # (16 atoms would take the kernel for few atoms: insist on the one the step ran, whose sums are bitwise
+        # independent of the atom count and of the grid)
+        forced = sweep_kernel == "timelag_chain_kernel" and "SOAP_TL_CHAIN" not in os.environ
+        if forced:
+            os.environ["SOAP_TL_CHAIN"] = "1"
         redo = timelag_device(samples[nb], WINDOWS, _lib.KIND_SIMPLE, 1, mult=mult)
+        if forced:
+            del os.environ["SOAP_TL_CHAIN"]
         idx = plan.index_device().long()
         xa = samples[nb][:, :4, :][..., idx]
         xa = xa / xa.norm(dim=-1, keepdim=True)

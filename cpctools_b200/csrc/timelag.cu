@@ -878,7 +878,9 @@ static ChainChoice chain_choose(int64_t F, int64_t A, int nw, const int *windows
   const int mode = env_int("SOAP_TL_CHAIN", kChainDefault);
   const bool on = mode == 1 || (mode < 0 && es == 8 && env_int("SOAP_TL_RB", -1) != 1 && env_int("SOAP_TL_PAIR", -1) != 1);
   if (!on || bulk_ok != 1 || nw < 2 || nw > 4 || kind == SOAP_KIND_EUCLID || kind == SOAP_KIND_EUCLID_NORMALIZED) return ch;
-  if (!tl_atom_major(A)) return ch;
+  // a CTA owns whole atoms here: with fewer than 4 atoms per SM the (atom, piece) items of timelag_kernel keep more
+  // SMs busy -- unless the caller insists (bench.py recomputes 16 atoms of a neighbour's shard BITWISE)
+  if (mode != 1 && !tl_atom_major(A)) return ch;
   int ring = -1, nc = 0, ci[3] = {0, 0, 0};
   for (int k = 0; k < nw; ++k) {
     const int w = windows[k];
@@ -912,7 +914,7 @@ static ChainChoice chain_choose(int64_t F, int64_t A, int nw, const int *windows
 
 template <typename T, int U, int SR, int NS, int C1, int C2, int C3, bool HM>
 static int launch_timelag_chain(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D, const ChainPlan &pl,
-                                const ChainChoice &ch, cudaStream_t s) {
+                                const ChainChoice &ch, int ov, cudaStream_t s) {
   // SR: 0 = shuffle butterfly, 1 = sums through shared memory, 2 + d = the same, loads pipelined d columns ahead
   auto kern = timelag_chain_kernel<T, U, NS, C1, C2, C3, HM, (SR > 0), (SR >= 2 ? SR - 2 : 0)>;
   SOAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -932,23 +934,28 @@ static int launch_timelag_chain(const void *X, const void *mult, double *scratch
   SOAP_REQUIRE(row_words < 2147483647LL, "soap_timelag: a frame of %lld bytes exceeds the tensor-map coordinate range", (long long)row_words * 8);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, pl.pitch / 8, kChB, CU_TENSOR_MAP_SWIZZLE_NONE,
+  CUtensorMap tmap_last;
+  memset(&tmap_last, 0, sizeof(tmap_last));
+  int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, pl.pitch / 8, kChB + ov, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_NONE);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tmap_last, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, pl.last_units * 2, kChB + ov, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE);
   if (rc) return rc;
   ProfScope prof(SOAP_PROF_TIMELAG, s);
   kern<<<(unsigned)grid, kChThreads, pl.smem, s>>>(static_cast<const T *>(mult), scratch, cta_acc, (long long)F, (long long)A, D, pl.split, pl.upp,
-                                                   pl.pitch, (int)pl.blk_bytes, pl.nbuf, ch.w0, tmap);
+                                                   pl.pitch, pl.last_units * 16, (int)pl.blk_bytes, pl.nbuf, ch.w0, ov, tmap, tmap_last);
   g_tl_last_kernel = "timelag_chain_kernel";
   return check_launch("timelag_chain_kernel");
 }
 
 template <typename T, int U, int SR>
 static int launch_chain_pattern(const void *X, const void *mult, double *scratch, int64_t F, int64_t A, int D, const ChainPlan &pl,
-                                const ChainChoice &ch, cudaStream_t s) {
+                                const ChainChoice &ch, int ov, cudaStream_t s) {
 #define CH_CASE(NS, C1, C2, C3)                                                                                   \
   if (ch.ns == NS && ch.c[0] == C1 && ch.c[1] == C2 && ch.c[2] == C3)                                             \
-    return mult ? launch_timelag_chain<T, U, SR, NS, C1, C2, C3, true>(X, mult, scratch, F, A, D, pl, ch, s)      \
-                : launch_timelag_chain<T, U, SR, NS, C1, C2, C3, false>(X, mult, scratch, F, A, D, pl, ch, s);
+    return mult ? launch_timelag_chain<T, U, SR, NS, C1, C2, C3, true>(X, mult, scratch, F, A, D, pl, ch, ov, s)  \
+                : launch_timelag_chain<T, U, SR, NS, C1, C2, C3, false>(X, mult, scratch, F, A, D, pl, ch, ov, s);
   CH_CASE(1, 1, 2, 10)
   CH_CASE(1, 1, 2, 0)
 #undef CH_CASE
@@ -1014,6 +1021,10 @@ extern "C" size_t soap_timelag_scratch_bytes(int64_t n_frames, int64_t n_atoms, 
   size_t bytes = tl_atom_major(n_atoms)
                      ? ((size_t)n_atoms * pl.Q * (size_t)n_frames + (size_t)tl_max_grid() * pl.Q * padded) * sizeof(double)
                      : (size_t)n_atoms * (size_t)(pl.split > pair_split ? pl.split : pair_split) * pl.Q * (size_t)n_frames * sizeof(double);
+  // the chain kernel forced on for a few atoms (SOAP_TL_CHAIN=1): totals + one accumulator per CTA (at most one per atom)
+  const size_t forced = ((size_t)n_atoms * pl.Q * (size_t)n_frames +
+                         (size_t)(n_atoms < tl_max_grid() ? n_atoms : tl_max_grid()) * pl.Q * padded) * sizeof(double);
+  if (forced > bytes) bytes = forced;
   return (bytes > rb_bytes ? bytes : rb_bytes) + tl_pad_bytes(dim, es) + tl_inv_bytes(n_frames, n_atoms);
 }
 
@@ -1073,14 +1084,16 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
     const ChainChoice cc = chain_choose(n_frames, n_atoms, n_windows, windows_host, kind, bulk_ok, es);
     ChainPlan cp;
     const int chU = env_int("SOAP_TL_CHAIN_U", 4);
-    const int chSR = env_int("SOAP_TL_CHAIN_SR", 4);
-    if (cc.use && whole_units && (chU == 3 || chU == 4) && ch_make_plan(dim, es, n_windows, chU, chSR != 0, cp)) {
+    const int chSR = env_int("SOAP_TL_CHAIN_SR", 1);
+    // SOAP_TL_CHAIN_OV=0: no overlapping boxes (the previous block is held back for the ring-window partners instead)
+    const int chOV = (cc.ns && cc.w0 <= 2 && env_int("SOAP_TL_CHAIN_OV", 1) != 0) ? cc.w0 : 0;
+    if (cc.use && whole_units && (chU == 3 || chU == 4) && ch_make_plan(dim, es, n_windows, chU, chSR != 0, chOV, cp)) {
 #define CH_VAR(UU, SS)                                                                                              \
   if (chU == UU && chSR == SS)                                                                                      \
-    rc = dtype == SOAP_F64 ? launch_chain_pattern<double, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, s)   \
-                           : launch_chain_pattern<float, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, s);
+    rc = dtype == SOAP_F64 ? launch_chain_pattern<double, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, chOV, s) \
+                           : launch_chain_pattern<float, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, chOV, s);
       rc = set_error(SOAP_EINVAL, "soap_timelag: no chain variant SOAP_TL_CHAIN_U=%d SOAP_TL_CHAIN_SR=%d", chU, chSR);
-      CH_VAR(4, 0) CH_VAR(4, 1) CH_VAR(4, 3) CH_VAR(4, 4) CH_VAR(4, 5) CH_VAR(3, 4)
+      CH_VAR(4, 4) CH_VAR(4, 1) CH_VAR(4, 0)
 #undef CH_VAR
       if (rc) return rc;
       int64_t off[4] = {0, 0, 0, 0};

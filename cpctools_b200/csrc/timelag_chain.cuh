@@ -34,21 +34,25 @@ constexpr int kChThreads = (kChS + 2) * 32;
 constexpr int kChRedPitch = 34;  // doubles per (frame, sum) row of the lanes' partial sums (32 + 2: conflict-free 128-bit reads)
 
 struct ChainPlan {
-  int unit_elems, n_units, split, upp, pitch, Q, nbuf;
+  int unit_elems, n_units, split, upp, pitch, last_units, Q, nbuf;
   size_t blk_bytes, smem;
 };
 
 // SR: the lanes' partial sums go through shared memory to the reducer warp (instead of the shuffle butterfly)
-static bool ch_make_plan(int D, int elem_size, int nw, int U, bool SR, ChainPlan &pl) {
+// ov: rows of the previous block fetched again in front of every box (the ring-window partners of a block's first
+// frames then sit in the block's own buffer and nothing is held back for them: one more block in flight)
+static bool ch_make_plan(int D, int elem_size, int nw, int U, bool SR, int ov, ChainPlan &pl) {
   pl.unit_elems = 16 / elem_size;
   if (D % pl.unit_elems) return false;
   pl.n_units = D / pl.unit_elems;
   pl.Q = 1 + nw;
+  // pieces of 32 * U units (every lane busy, and 512 * U bytes apart: box rows start and end on 64-byte DRAM atoms
+  // whenever the rows themselves do) + a narrower last piece with its own tensor map (dense box rows: its own pitch)
   pl.split = (pl.n_units + 32 * U - 1) / (32 * U);
-  pl.upp = (pl.n_units + pl.split - 1) / pl.split;
-  pl.split = (pl.n_units + pl.upp - 1) / pl.upp;  // no empty pieces
+  pl.upp = pl.split > 1 ? 32 * U : pl.n_units;
+  pl.last_units = pl.n_units - (pl.split - 1) * pl.upp;
   pl.pitch = 16 * pl.upp;
-  pl.blk_bytes = align_up((size_t)kChB * pl.pitch, 128);  // TMA destinations are 128-byte aligned
+  pl.blk_bytes = align_up((size_t)(kChB + ov) * pl.pitch, 128);  // TMA destinations are 128-byte aligned
   for (pl.nbuf = kChNbufMax; pl.nbuf >= 3; --pl.nbuf) {
     pl.smem = (size_t)pl.nbuf * pl.blk_bytes + (size_t)2 * kChB * pl.Q * 8 * (SR ? kChRedPitch : 1) + (size_t)(2 * kChNbufMax + 4) * 8 + 64;
     if (pl.smem <= (size_t)max_smem_optin() - 1024) return true;
@@ -128,13 +132,13 @@ template <> struct ChVec<double> { using type = double2; };
 template <> struct ChVec<float> { using type = float4; };
 
 template <int N, int U, int NS, int C1, int C2, int C3, int Q>
-__device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, const uint32_t (&col)[U], const bool (&act)[U],
+__device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, const uint32_t col, const bool (&act)[U],
                                             const double2 (&m)[U], double2 (&h)[kChH][U], double (&v)[Q]) {
   double2 x[U], p[U];
 #pragma unroll
   for (int c = 0; c < U; ++c) {
-    x[c] = act[c] ? lds_d2(x_addr + col[c]) : make_double2(0.0, 0.0);
-    if (NS) p[c] = act[c] ? lds_d2(p_addr + col[c]) : make_double2(0.0, 0.0);
+    x[c] = act[c] ? lds_d2(x_addr + col + 512u * c) : make_double2(0.0, 0.0);
+    if (NS) p[c] = act[c] ? lds_d2(p_addr + col + 512u * c) : make_double2(0.0, 0.0);
   }
   double s[Q][2];
 #pragma unroll
@@ -177,13 +181,13 @@ __device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, co
 // fp32 data: products and two 2U-term chains per sum in fp32, promoted to double before the cross-lane sum (the same
 // accuracy class as accum_units_f32: the fp32 rounding is bounded to one short chain)
 template <int N, int U, int NS, int C1, int C2, int C3, int Q>
-__device__ __forceinline__ void ch_step_f32(uint32_t x_addr, uint32_t p_addr, const uint32_t (&col)[U], const bool (&act)[U],
+__device__ __forceinline__ void ch_step_f32(uint32_t x_addr, uint32_t p_addr, const uint32_t col, const bool (&act)[U],
                                             const float4 (&m)[U], float4 (&h)[kChH][U], double (&v)[Q]) {
   float4 x[U], p[U];
 #pragma unroll
   for (int c = 0; c < U; ++c) {
-    x[c] = act[c] ? lds_f4(x_addr + col[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (NS) p[c] = act[c] ? lds_f4(p_addr + col[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    x[c] = act[c] ? lds_f4(x_addr + col + 512u * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NS) p[c] = act[c] ? lds_f4(p_addr + col + 512u * c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float s[Q][2];
 #pragma unroll
@@ -245,6 +249,8 @@ __device__ __forceinline__ void ch_col(const double2 &x, const double2 &p, const
 }
 template <int N, int C, int U, int NS, int C1, int C2, int C3, int Q>
 __device__ __forceinline__ void ch_col(const float4 &x, const float4 &p, const float4 &m, float4 (&h)[kChH][U], float (&s)[Q][2]) {
+  // (packed FFMA2 / FMUL2 need aligned register pairs: at the 255-register cap they spill, measured 0.46-0.48 of the
+  // HBM peak against 0.61-0.68 unpacked)
   auto dot = [](const float4 &a, const float4 &b, float (&acc)[2]) {
     acc[0] = fmaf(a.x, b.x, acc[0]);
     acc[1] = fmaf(a.y, b.y, acc[1]);
@@ -278,7 +284,8 @@ __device__ __forceinline__ void ch_static_for(F &&f, std::integer_sequence<int, 
 template <typename T, int U, int NS, int C1, int C2, int C3, bool HAS_MULT, bool SR, int PD>
 __global__ void __launch_bounds__(kChThreads, 1)
     timelag_chain_kernel(const T *__restrict__ mult, double *__restrict__ sums, double *__restrict__ cta_acc, long long F, long long A,
-                         int D, int split, int upp, int pitch, int blk_bytes, int nbuf, int w0, const __grid_constant__ CUtensorMap tmap) {
+                         int D, int split, int upp, int pitch_full, int pitch_last, int blk_bytes, int nbuf, int w0, int ov,
+                         const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_last) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using V = typename ChVec<T>::type;
   constexpr int UE = 16 / (int)sizeof(T);
@@ -315,12 +322,14 @@ __global__ void __launch_bounds__(kChThreads, 1)
     int s = 0, ph = 0, g = 0;
     for (int k = 0; k < n_my; ++k) {
       const TlItem it = tl_item<UE>(k, split, upp, D, true, false);
+      const bool last = it.p == split - 1;
       for (int b = 0; b < nblk; ++b, ++g) {
         if (g >= nbuf) mbar_wait(&empty[s], (uint32_t)(ph ^ 1));
         if (lane == 0) {
-          // rows beyond F and columns beyond the tensor are zero-filled and still counted in the transaction bytes
-          mbar_expect_tx(&full[s], (uint32_t)kChB * (uint32_t)pitch);
-          tma_load_2d(ring + (size_t)s * blk_bytes, &tmap, (int)it.w0, b * kChB, &full[s]);
+          // rows beyond F are zero-filled and still counted in the transaction bytes
+          // (and so are the rows -ov .. -1 in front of an item's first block)
+          mbar_expect_tx(&full[s], (uint32_t)(kChB + ov) * (uint32_t)(last ? pitch_last : pitch_full));
+          tma_load_2d(ring + (size_t)s * blk_bytes, last ? &tmap_last : &tmap, (int)it.w0, b * kChB - ov, &full[s]);
         }
         if (++s == nbuf) s = 0, ph ^= 1;
       }
@@ -413,13 +422,11 @@ __global__ void __launch_bounds__(kChThreads, 1)
         if constexpr (sizeof(T) == 8) h[n][c] = make_double2(0.0, 0.0);
         else h[n][c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    uint32_t col[U];
-#pragma unroll
-    for (int c = 0; c < U; ++c) col[c] = 16u * (uint32_t)(lane + 32 * c);
+    const uint32_t col = 16u * (uint32_t)lane;  // column c of the lane: + 512 c
     int s = 0, ph = 0, g = 0;
 
     // one block = kChSteps chain steps, history slots HALF * kChSteps + j (static)
-    auto block = [&](auto half, const bool (&act)[U], const V (&m)[U]) {
+    auto block = [&](auto half, const bool (&act)[U], const V (&m)[U], const int pitch) {
       constexpr int HALF = decltype(half)::value;
       const uint32_t cur = ring_addr + (uint32_t)s * (uint32_t)blk_bytes;
       const uint32_t prv = ring_addr + (uint32_t)(s == 0 ? nbuf - 1 : s - 1) * (uint32_t)blk_bytes;
@@ -435,11 +442,11 @@ __global__ void __launch_bounds__(kChThreads, 1)
         S sacc[Q][2];
         auto load = [&](auto tt) {
           constexpr int TT = decltype(tt)::value, J = TT / U, C = TT % U;
-          const int fl = kChS * J + warp;  // frame within the block
-          const int pl = fl - w0;          // its ring-window partner: this block or the previous one (w0 <= 25)
-          ch_lds(xq[TT % NSLOT], cur + (uint32_t)fl * (uint32_t)pitch + col[C], act[C]);
+          const int fl = kChS * J + warp + ov;  // row of the frame in the block's buffer
+          const int pl = fl - w0;               // its ring-window partner: this buffer or the previous one (w0 <= 25)
+          ch_lds(xq[TT % NSLOT], cur + (uint32_t)fl * (uint32_t)pitch + col + 512u * C, act[C]);
           if (NS)
-            ch_lds(pq[TT % NSLOT], (pl >= 0 ? cur + (uint32_t)pl * (uint32_t)pitch : prv + (uint32_t)(pl + kChB) * (uint32_t)pitch) + col[C], act[C]);
+            ch_lds(pq[TT % NSLOT], (pl >= 0 ? cur + (uint32_t)pl * (uint32_t)pitch : prv + (uint32_t)(pl + kChB) * (uint32_t)pitch) + col + 512u * C, act[C]);
         };
         ch_static_for(load, std::make_integer_sequence<int, (PD < NT ? PD : NT)>{});
         auto task = [&](auto tt) {
@@ -461,10 +468,10 @@ __global__ void __launch_bounds__(kChThreads, 1)
       auto step = [&](auto jj) {
         constexpr int J = decltype(jj)::value;
         const int fl = kChS * J + warp;  // frame within the block
-        const uint32_t x_addr = cur + (uint32_t)fl * (uint32_t)pitch;
-        // ring-window partner: frame fl - w0 of this block, or of the previous one (w0 <= 25; the first frames of an
-        // item read the previous item's last frames there: results for f < w0 are never used)
-        const int pl = fl - w0;
+        const uint32_t x_addr = cur + (uint32_t)(fl + ov) * (uint32_t)pitch;
+        // ring-window partner: row fl + ov - w0 of this buffer, or of the previous one (w0 <= 25, ov = 0; the first
+        // frames of an item read the previous item's last frames there: results for f < w0 are never used)
+        const int pl = fl + ov - w0;
         const uint32_t p_addr = pl >= 0 ? cur + (uint32_t)pl * (uint32_t)pitch : prv + (uint32_t)(pl + kChB) * (uint32_t)pitch;
         double v[Q];
         if constexpr (sizeof(T) == 8)
@@ -489,7 +496,10 @@ __global__ void __launch_bounds__(kChThreads, 1)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&red_full[g & 1]);
-        if (g >= 1) mbar_arrive(&empty[s == 0 ? nbuf - 1 : s - 1]);
+        if (ov)
+          mbar_arrive(&empty[s]);  // (ov == w0: nothing of this buffer is needed again)
+        else if (g >= 1)
+          mbar_arrive(&empty[s == 0 ? nbuf - 1 : s - 1]);
       }
       if (++s == nbuf) s = 0, ph ^= 1;
       ++g;
@@ -511,9 +521,12 @@ __global__ void __launch_bounds__(kChThreads, 1)
           if (HAS_MULT && act[c]) m[c] = *reinterpret_cast<const float4 *>(mult + it.e0 + (lane + 32 * c) * UE);
         }
       }
+      // (the first block of an item reads its ring-window partners from the previous ITEM's last block with this
+      // item's pitch: garbage either way, and never used)
+      const int pitch = it.p == split - 1 ? pitch_last : pitch_full;
       for (int b = 0; b < nblk; b += 2) {
-        block(std::integral_constant<int, 0>{}, act, m);
-        if (b + 1 < nblk) block(std::integral_constant<int, 1>{}, act, m);
+        block(std::integral_constant<int, 0>{}, act, m, pitch);
+        if (b + 1 < nblk) block(std::integral_constant<int, 1>{}, act, m, pitch);
       }
     }
   }

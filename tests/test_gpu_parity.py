@@ -448,6 +448,7 @@ def test_timelag_two_frames_per_lane_kernel(S, F, A, D, dtype, windows, monkeypa
         (77, 640, 200, np.float32, (50, 1, 10, 5)),     # one piece of 50 units, windows in any order
         (26, 600, 1728, np.float32, (2, 10, 5)),        # two blocks, the second nearly empty; four pieces
         (120, 592, 516, np.float64, (25, 5, 10, 50)),   # the largest ring window; two full columns + a ragged one
+        (230, 5, 1224, np.float64, (1, 5, 10, 50)),     # forced on for a handful of atoms (bench.py's neighbour check)
     ],
 )
 def test_timelag_chain_kernel(S, F, A, D, dtype, windows, monkeypatch):
