@@ -944,7 +944,7 @@ static int launch_timelag_chain(const void *X, const void *mult, double *scratch
   if (rc) return rc;
   ProfScope prof(SOAP_PROF_TIMELAG, s);
   kern<<<(unsigned)grid, kChThreads, pl.smem, s>>>(static_cast<const T *>(mult), scratch, cta_acc, (long long)F, (long long)A, D, pl.split, pl.upp,
-                                                   pl.pitch, pl.last_units * 16, (int)pl.blk_bytes, pl.nbuf, ch.w0, ov, tmap, tmap_last);
+                                                   pl.pitch, pl.last_units * 16, (int)pl.blk_bytes, pl.nbuf, ch.w0, ov, env_int("SOAP_TL_CHAIN_RED", 2) == 1 ? 1 : 2, tmap, tmap_last);
   g_tl_last_kernel = "timelag_chain_kernel";
   return check_launch("timelag_chain_kernel");
 }

@@ -30,7 +30,8 @@ constexpr int kChH = 10;     // chain steps of history in registers (windows up 
 constexpr int kChSteps = 5;  // chain steps per block
 constexpr int kChB = kChS * kChSteps;  // frames per block (25)
 constexpr int kChNbufMax = 4;  // ring blocks: previous (window-1 partner of a block's first frames), current, 1-2 in flight
-constexpr int kChThreads = (kChS + 2) * 32;
+constexpr int kChRed = 2;     // reducer warps in the CTA (the launch decides how many of them work: nred)
+constexpr int kChThreads = (kChS + 1 + kChRed) * 32;
 constexpr int kChRedPitch = 34;  // doubles per (frame, sum) row of the lanes' partial sums (32 + 2: conflict-free 128-bit reads)
 
 struct ChainPlan {
@@ -275,7 +276,10 @@ __device__ __forceinline__ void ch_static_for(F &&f, std::integer_sequence<int, 
 }
 
 // Warp roles: warps 0..4 consume (warp = frame mod 5, lane = units), warp 5 produces (one tensor-map box of 25 frames
-// x one piece per block), warp 6 adds the pieces of an atom (L2-resident per-CTA accumulator, as timelag_kernel).
+// x one piece per block), warps 6 and 7 add the lanes' partial sums and the pieces of an atom (L2-resident per-CTA
+// accumulator, as timelag_kernel); with one reducer warp it was 81 % busy and the consumers waited for it 10 % of
+// their time (profiles/r03_timelag_chain_ncu_full.txt), with two the sweep is ~4 % faster once the GPU is power capped
+// (SOAP_TL_CHAIN_RED=1 | 2, interleaved A/B in profiles/r03_timelag_chain_ab2.txt).
 //   full[s]        producer -> consumers   block in ring buffer s has landed
 //   empty[s]       consumers -> producer   buffer s is no longer needed (arrived at the END of the following block:
 //                                          its first frames read their ring-window partners from buffer s)
@@ -284,7 +288,7 @@ __device__ __forceinline__ void ch_static_for(F &&f, std::integer_sequence<int, 
 template <typename T, int U, int NS, int C1, int C2, int C3, bool HAS_MULT, bool SR, int PD>
 __global__ void __launch_bounds__(kChThreads, 1)
     timelag_chain_kernel(const T *__restrict__ mult, double *__restrict__ sums, double *__restrict__ cta_acc, long long F, long long A,
-                         int D, int split, int upp, int pitch_full, int pitch_last, int blk_bytes, int nbuf, int w0, int ov,
+                         int D, int split, int upp, int pitch_full, int pitch_last, int blk_bytes, int nbuf, int w0, int ov, int nred,
                          const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_last) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using V = typename ChVec<T>::type;
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(kChThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&red_full[i], kChS);
-      mbar_init(&red_empty[i], 1);
+      mbar_init(&red_empty[i], nred);
     }
     fence_mbar_init();
   }
@@ -334,8 +338,11 @@ __global__ void __launch_bounds__(kChThreads, 1)
         if (++s == nbuf) s = 0, ph ^= 1;
       }
     }
-  } else if (warp == kChS + 1) {
-    // ===== reducer: adds the pieces of an atom, lane = frame of the block ==============================================
+  } else if (warp > kChS + nred) {
+    // (a reducer warp the launch does not use)
+  } else if (warp > kChS) {
+    // ===== reducers: add the lanes' partial sums, then the pieces of an atom ============================================
+    const int rw = warp - (kChS + 1);  // each reducer warp takes its share of a block's (frame, sum) pairs
     int g = 0;
     const uint64_t pol = l2_policy_evict_last();
     for (int k = 0; k < n_my; ++k) {
@@ -347,14 +354,14 @@ __global__ void __launch_bounds__(kChThreads, 1)
         if constexpr (SR) {
           // lane <-> (frame, sum) pair of the block, 32 pairs per round: adds the 32 lanes' partial sums in a fixed
           // tree (16 pair sums, 4 chains of 4, 2 + 1), then the pieces of the atom
-          constexpr int NP = kChB * Q, ROUNDS = (NP + 31) / 32;
+          constexpr int NP = kChB * Q, ROUNDS = (NP + 31) / 32;  // round rd belongs to reducer warp rd % nred
           double prev[ROUNDS];
           size_t where[ROUNDS];
           long long fls[ROUNDS];
           int qs[ROUNDS];
 #pragma unroll
           for (int rd = 0; rd < ROUNDS; ++rd) {
-            const int pi = rd * 32 + lane, fb = pi / Q;
+            const int pi = (rd % nred == rw) ? rd * 32 + lane : NP, fb = pi / Q;
             qs[rd] = pi - fb * Q;
             fls[rd] = (long long)b * kChB + fb;
             where[rd] = (size_t)qs[rd] * nblk * kChB + (size_t)fls[rd];
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(kChThreads, 1)
           const uint32_t rbase = smem_u32(red) + (uint32_t)(g & 1) * (uint32_t)(NP * kChRedPitch * 8);
 #pragma unroll
           for (int rd = 0; rd < ROUNDS; ++rd) {
-            const int pi = rd * 32 + lane;
+            const int pi = (rd % nred == rw) ? rd * 32 + lane : NP;
             if (pi < NP) {
               const uint32_t ra = rbase + (uint32_t)pi * (uint32_t)(kChRedPitch * 8);
               double e[16];
@@ -390,9 +397,9 @@ __global__ void __launch_bounds__(kChThreads, 1)
           double prev[Q];
 #pragma unroll
           for (int q = 0; q < Q; ++q)
-            prev[q] = (first_piece || lane >= kChB) ? 0.0 : ld_acc(acc_row + (size_t)q * nblk * kChB + fl, pol);
+            prev[q] = (first_piece || lane >= kChB || rw != 0) ? 0.0 : ld_acc(acc_row + (size_t)q * nblk * kChB + fl, pol);
           mbar_wait(&red_full[g & 1], (uint32_t)((g >> 1) & 1));
-          if (lane < kChB) {
+          if (lane < kChB && rw == 0) {  // (the butterfly leaves one value per frame and sum: one reducer warp does it)
             const double *r = red + ((size_t)(g & 1) * kChB + lane) * Q;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
