@@ -880,7 +880,12 @@ static ChainChoice chain_choose(int64_t F, int64_t A, int nw, const int *windows
   if (!on || bulk_ok != 1 || nw < 2 || nw > 4 || kind == SOAP_KIND_EUCLID || kind == SOAP_KIND_EUCLID_NORMALIZED) return ch;
   // a CTA owns whole atoms here: with fewer than 4 atoms per SM the (atom, piece) items of timelag_kernel keep more
   // SMs busy -- unless the caller insists (bench.py recomputes 16 atoms of a neighbour's shard BITWISE)
-  if (mode != 1 && !tl_atom_major(A)) return ch;
+  if (mode != 1 && !tl_atom_major(A)) {
+    // ... or when whole atoms fill the SMs evenly enough (148 atoms: one each, 0.94 of the HBM peak against 0.75; 400: 0.89 against 0.73)
+    const long long sms = persistent_sms() > 0 ? persistent_sms() : 1;
+    const double busy = (double)A / (double)(((A + sms - 1) / sms) * sms);
+    if (busy < 0.72) return ch;  // (break-even measured at 200 atoms = 0.68: profiles/r03_timelag_chain_small_a.txt)
+  }
   int ring = -1, nc = 0, ci[3] = {0, 0, 0};
   for (int k = 0; k < nw; ++k) {
     const int w = windows[k];

@@ -1288,3 +1288,54 @@ def test_fuzz_timelag_raw_dimensions_and_kinds(S):
                 warnings.simplefilter("ignore")
                 want, _ = O.timeSOAP_batched(Xw, window=w, kind=okind, power=power)
             assert_distance_parity(t.cpu().numpy(), want, path, what=f"case {case} {name} F{F} A{A} D{D} w{w}")
+
+
+def test_fuzz_timelag_chain_kernel(S, monkeypatch):
+    """24 seeded random trajectories through the lane = units sweep kernel (timelag_chain.cuh) forced on: whole-unit
+    rows from a single unit to five pieces, any number of frames above the largest window (one block, odd and even
+    block counts), few and many atoms per CTA, every cosine-type kind, both dtypes, ring windows 1..25 in either
+    pattern and any order, with and without multiplicities -- against the batched oracle, and the kernel must really
+    have been the one that ran."""
+    import torch
+    from cpctools_b200 import _lib
+    from cpctools_b200.analysis import timelag_device
+
+    monkeypatch.setenv("SOAP_TL_CHAIN", "1")
+    rng = np.random.default_rng(777 + _fuzz_offset())
+    kinds = [("simple", _lib.KIND_SIMPLE, O.KIND_SIMPLE, 1), ("kernel1", _lib.KIND_KERNEL, O.KIND_KERNEL, 1),
+             ("kernel2", _lib.KIND_KERNEL, O.KIND_KERNEL, 2), ("normalized", _lib.KIND_NORMALIZED, O.KIND_NORMALIZED, 1)]
+    ring_choices = [w for w in range(1, 26) if w % 5]
+    for case in range(24):
+        dtype = [np.float64, np.float32][case % 2]
+        ue = 2 if dtype == np.float64 else 4
+        four = case % 3 != 0
+        w0 = int(rng.choice(ring_choices)) if case % 4 else 1
+        windows = [w0, 5, 10] + ([50] if four else [])
+        rng.shuffle(windows)
+        windows = tuple(int(w) for w in windows)
+        F = int(rng.integers(max(windows) + 1, max(windows) + 120))
+        A = int(rng.integers(1, 40)) if case % 5 else int(rng.integers(300, 700))
+        units = int(rng.choice([1, 7, 31, 32, 33, 100, 128, 129, 200, 306, 500, 612, 640]))
+        if A > 100:
+            units = min(units, 64)
+        D = units * ue
+        path = "f64" if dtype == np.float64 else "f32_timelag"
+        name, kind, okind, power = kinds[case % 4]
+        X = (rng.random((F, A, D)) + 0.05).astype(dtype)
+        X64 = X.astype(np.float64)
+        if name == "normalized":
+            X64 = O.normalizeArray(X64)
+            X = X64.astype(dtype)
+            X64 = X.astype(np.float64)
+        use_mult = case % 3 != 1
+        m = (1.0 + (rng.random(D) < 0.5)).astype(dtype) if use_mult else None
+        ts = timelag_device(torch.from_numpy(X).cuda(), windows, kind, power,
+                            mult=None if m is None else torch.from_numpy(m).cuda())
+        assert _lib.load().soap_timelag_last_kernel() == b"timelag_chain_kernel", (case, windows, F, A, D)
+        Xw = X64 if m is None else X64 * np.sqrt(m.astype(np.float64))
+        for w, t in zip(windows, ts):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want, _ = O.timeSOAP_batched(Xw, window=w, kind=okind, power=power)
+            assert t.shape == (F - w, A)
+            assert_distance_parity(t.cpu().numpy(), want, path, what=f"case {case} {name} F{F} A{A} D{D} windows {windows} w{w}")
