@@ -46,6 +46,14 @@ def main():
             for w, t in zip((1, 5, 10, 50), got):
                 e2, rel = err(t, O.timeSOAP_batched(ref, window=w, returnDiff=False), dmin)
                 line(f"timeSOAP fused-from-compressed  data {kind} {path} window {w}", e2, rel, tol)
+            # the same through the lane = units kernel (timelag_chain.cuh; the default for float64 sweeps over many atoms)
+            os.environ["SOAP_TL_CHAIN"] = "1"
+            got = S.timeSOAPfromCompressed(raw.astype(dt), 8, 8, ["H", "O"], sl, windows=(1, 5, 10, 50), returnDiff=False)
+            del os.environ["SOAP_TL_CHAIN"]
+            assert _lib.load().soap_timelag_last_kernel() == b"timelag_chain_kernel"
+            for w, t in zip((1, 5, 10, 50), got):
+                e2, rel = err(t, O.timeSOAP_batched(ref, window=w, returnDiff=False), dmin)
+                line(f"timeSOAP fused-from-compressed  data {kind} {path} window {w}  (chain kernel)", e2, rel, tol)
         t = S.timeSOAP(X, window=1, returnDiff=False)
         e2, rel = err(t, O.timeSOAP_batched(X, window=1, returnDiff=False), 0.1)
         line(f"timeSOAP materialised 1728       data {kind} f64 window 1", e2, rel, 1e-12)
