@@ -1091,8 +1091,14 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
     const int chU = env_int("SOAP_TL_CHAIN_U", 4);
     const int chSR = env_int("SOAP_TL_CHAIN_SR", 1);
     // SOAP_TL_CHAIN_OV=0: no overlapping boxes (the previous block is held back for the ring-window partners instead)
-    const int chOV = (cc.ns && cc.w0 <= 2 && env_int("SOAP_TL_CHAIN_OV", 1) != 0) ? cc.w0 : 0;
-    if (cc.use && whole_units && (chU == 3 || chU == 4) && ch_make_plan(dim, es, n_windows, chU, chSR != 0, chOV, cp)) {
+    // (window 2 with full-width pieces: three buffers of 27 rows do not fit beside the partial sums -> no overlap)
+    int chOV = (cc.ns && cc.w0 <= 2 && env_int("SOAP_TL_CHAIN_OV", 1) != 0) ? cc.w0 : 0;
+    bool ch_ok = cc.use && whole_units && (chU == 3 || chU == 4);
+    if (ch_ok && !ch_make_plan(dim, es, n_windows, chU, chSR != 0, chOV, cp)) {
+      chOV = 0;
+      ch_ok = ch_make_plan(dim, es, n_windows, chU, chSR != 0, chOV, cp);
+    }
+    if (ch_ok) {
 #define CH_VAR(UU, SS)                                                                                              \
   if (chU == UU && chSR == SS)                                                                                      \
     rc = dtype == SOAP_F64 ? launch_chain_pattern<double, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, chOV, s) \
