@@ -863,6 +863,8 @@ static int launch_timelag_pair(const void *X, const void *mult, double *scratch,
 
 // ---- lane = units, lag history in registers (timelag_chain.cuh) ------------------------------------------------------
 // SOAP_TL_CHAIN_U = 3 | 4 units per lane, SOAP_TL_CHAIN_SR = 1 | 0: partial sums through shared memory | by shuffles
+// (ring window?, chain windows / 5): (w0, 5, 50), (w0, 10, 50), (w0, 5, 10, 25), (w0, 5, 10, 20), (5, 10, 50), (5, 10, 25)
+#define CH_MORE_PATTERNS CH_MORE(1, 1, 10, 0) CH_MORE(1, 2, 10, 0) CH_MORE(1, 1, 2, 5) CH_MORE(1, 1, 2, 4) CH_MORE(0, 1, 2, 10) CH_MORE(0, 1, 2, 5)
 struct ChainChoice {
   bool use;
   int nw, ns, w0, c[3];  // ring window (ns = 1) and chain windows c[k] * 5, ascending
@@ -913,7 +915,14 @@ static ChainChoice chain_choose(int64_t F, int64_t A, int nw, const int *windows
   // instantiated patterns (launch_chain_pattern)
   const bool p4 = ch.ns == 1 && ch.c[0] == 1 && ch.c[1] == 2 && ch.c[2] == 10;  // (w0, 5, 10, 50)
   const bool p3 = ch.ns == 1 && ch.c[0] == 1 && ch.c[1] == 2 && ch.c[2] == 0;   // (w0, 5, 10)
-  ch.use = p4 || p3;
+  // further patterns, float64 and the default variant only (every pattern is an instantiation of its own)
+  bool more = false;
+  if (es == 8 && env_int("SOAP_TL_CHAIN_SR", 1) == 1 && env_int("SOAP_TL_CHAIN_U", 4) == 4 && nw >= 3) {
+#define CH_MORE(NS, C1, C2, C3) more = more || (ch.ns == NS && ch.c[0] == C1 && ch.c[1] == C2 && ch.c[2] == C3);
+    CH_MORE_PATTERNS
+#undef CH_MORE
+  }
+  ch.use = p4 || p3 || more;
   return ch;
 }
 
@@ -963,6 +972,11 @@ static int launch_chain_pattern(const void *X, const void *mult, double *scratch
                 : launch_timelag_chain<T, U, SR, NS, C1, C2, C3, false>(X, mult, scratch, F, A, D, pl, ch, ov, s);
   CH_CASE(1, 1, 2, 10)
   CH_CASE(1, 1, 2, 0)
+  if constexpr (std::is_same<T, double>::value && U == 4 && SR == 1) {
+#define CH_MORE(NS, C1, C2, C3) CH_CASE(NS, C1, C2, C3)
+    CH_MORE_PATTERNS
+#undef CH_MORE
+  }
 #undef CH_CASE
   return set_error(SOAP_EINVAL, "soap_timelag: no chain variant for this window pattern");
 }
@@ -1104,7 +1118,7 @@ extern "C" int soap_timelag(const void *X, const void *mult, double *t, const in
     rc = dtype == SOAP_F64 ? launch_chain_pattern<double, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, chOV, s) \
                            : launch_chain_pattern<float, UU, SS>(X, mult, sc, n_frames, n_atoms, dim, cp, cc, chOV, s);
       rc = set_error(SOAP_EINVAL, "soap_timelag: no chain variant SOAP_TL_CHAIN_U=%d SOAP_TL_CHAIN_SR=%d", chU, chSR);
-      CH_VAR(4, 4) CH_VAR(4, 1) CH_VAR(4, 0)
+      CH_VAR(4, 4) CH_VAR(4, 1)
 #undef CH_VAR
       if (rc) return rc;
       int64_t off[4] = {0, 0, 0, 0};

@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(kChThreads, 1)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&red_full[g & 1]);
-        if (ov)
-          mbar_arrive(&empty[s]);  // (ov == w0: nothing of this buffer is needed again)
+        if (ov || NS == 0)
+          mbar_arrive(&empty[s]);  // (ov == w0, or no ring window at all: nothing of this buffer is needed again)
         else if (g >= 1)
           mbar_arrive(&empty[s == 0 ? nbuf - 1 : s - 1]);
       }

@@ -1311,6 +1311,8 @@ def test_fuzz_timelag_chain_kernel(S, monkeypatch):
         four = case % 3 != 0
         w0 = int(rng.choice(ring_choices)) if case % 4 else 1
         windows = [w0, 5, 10] + ([50] if four else [])
+        if dtype == np.float64 and case % 8 >= 4:  # the further float64 patterns (chain_choose)
+            windows = [[w0, 5, 50], [w0, 10, 50], [w0, 5, 10, 25], [w0, 5, 10, 20], [5, 10, 50], [5, 10, 25]][int(rng.integers(0, 6))]
         rng.shuffle(windows)
         windows = tuple(int(w) for w in windows)
         F = int(rng.integers(max(windows) + 1, max(windows) + 120))
