@@ -42,7 +42,11 @@ struct ChainPlan {
 // SR: the lanes' partial sums go through shared memory to the reducer warp (instead of the shuffle butterfly)
 // ov: rows of the previous block fetched again in front of every box (the ring-window partners of a block's first
 // frames then sit in the block's own buffer and nothing is held back for them: one more block in flight)
-static bool ch_make_plan(int D, int elem_size, int nw, int U, bool SR, int ov, ChainPlan &pl) {
+// halo: instead of fetching that row again, the warp of chain 4 hands the LAST frame of every block (which it holds in
+// registers) to chain 0 through a small shared-memory area (4 x one piece): the boxes do not overlap (ov = 0) and
+// nothing is held back either
+constexpr int kChHalo = 4;  // halo buffers (the writer can be at most two blocks ahead of the reader)
+static bool ch_make_plan(int D, int elem_size, int nw, int U, bool SR, int ov, bool halo, ChainPlan &pl) {
   pl.unit_elems = 16 / elem_size;
   if (D % pl.unit_elems) return false;
   pl.n_units = D / pl.unit_elems;
@@ -55,7 +59,8 @@ static bool ch_make_plan(int D, int elem_size, int nw, int U, bool SR, int ov, C
   pl.pitch = 16 * pl.upp;
   pl.blk_bytes = align_up((size_t)(kChB + ov) * pl.pitch, 128);  // TMA destinations are 128-byte aligned
   for (pl.nbuf = kChNbufMax; pl.nbuf >= 3; --pl.nbuf) {
-    pl.smem = (size_t)pl.nbuf * pl.blk_bytes + (size_t)2 * kChB * pl.Q * 8 * (SR ? kChRedPitch : 1) + (size_t)(2 * kChNbufMax + 4) * 8 + 64;
+    pl.smem = (size_t)pl.nbuf * pl.blk_bytes + (size_t)2 * kChB * pl.Q * 8 * (SR ? kChRedPitch : 1) + (halo ? (size_t)kChHalo * 512 * U : 0) +
+              (size_t)(2 * kChNbufMax + 4 + kChHalo) * 8 + 64;
     if (pl.smem <= (size_t)max_smem_optin() - 1024) return true;
   }
   return false;
@@ -134,12 +139,17 @@ template <> struct ChVec<float> { using type = float4; };
 
 template <int N, int U, int NS, int C1, int C2, int C3, int Q>
 __device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, const uint32_t col, const bool (&act)[U],
-                                            const double2 (&m)[U], double2 (&h)[kChH][U], double (&v)[Q]) {
+                                            const double2 (&m)[U], double2 (&h)[kChH][U], double (&v)[Q], const uint32_t halo_st = 0) {
   double2 x[U], p[U];
 #pragma unroll
   for (int c = 0; c < U; ++c) {
     x[c] = act[c] ? lds_d2(x_addr + col + 512u * c) : make_double2(0.0, 0.0);
     if (NS) p[c] = act[c] ? lds_d2(p_addr + col + 512u * c) : make_double2(0.0, 0.0);
+  }
+  if (halo_st) {  // the last frame of the block, for the first frame of the next one (chain 0)
+#pragma unroll
+    for (int c = 0; c < U; ++c)
+      asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(halo_st + col + 512u * c), "d"(x[c].x), "d"(x[c].y) : "memory");
   }
   double s[Q][2];
 #pragma unroll
@@ -183,12 +193,17 @@ __device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, co
 // accuracy class as accum_units_f32: the fp32 rounding is bounded to one short chain)
 template <int N, int U, int NS, int C1, int C2, int C3, int Q>
 __device__ __forceinline__ void ch_step_f32(uint32_t x_addr, uint32_t p_addr, const uint32_t col, const bool (&act)[U],
-                                            const float4 (&m)[U], float4 (&h)[kChH][U], double (&v)[Q]) {
+                                            const float4 (&m)[U], float4 (&h)[kChH][U], double (&v)[Q], const uint32_t halo_st = 0) {
   float4 x[U], p[U];
 #pragma unroll
   for (int c = 0; c < U; ++c) {
     x[c] = act[c] ? lds_f4(x_addr + col + 512u * c) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (NS) p[c] = act[c] ? lds_f4(p_addr + col + 512u * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (halo_st) {
+#pragma unroll
+    for (int c = 0; c < U; ++c)
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(halo_st + col + 512u * c), "f"(x[c].x), "f"(x[c].y), "f"(x[c].z), "f"(x[c].w) : "memory");
   }
   float s[Q][2];
 #pragma unroll
@@ -288,7 +303,7 @@ __device__ __forceinline__ void ch_static_for(F &&f, std::integer_sequence<int, 
 template <typename T, int U, int NS, int C1, int C2, int C3, bool HAS_MULT, bool SR, int PD>
 __global__ void __launch_bounds__(kChThreads, 1)
     timelag_chain_kernel(const T *__restrict__ mult, double *__restrict__ sums, double *__restrict__ cta_acc, long long F, long long A,
-                         int D, int split, int upp, int pitch_full, int pitch_last, int blk_bytes, int nbuf, int w0, int ov, int nred,
+                         int D, int split, int upp, int pitch_full, int pitch_last, int blk_bytes, int nbuf, int w0, int ov, int nred, int halo,
                          const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_last) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using V = typename ChVec<T>::type;
@@ -299,10 +314,12 @@ __global__ void __launch_bounds__(kChThreads, 1)
   constexpr int RP = SR ? kChRedPitch : 1;
   unsigned char *ring = smem_raw;                                                          // [nbuf][blk_bytes]
   double *red = reinterpret_cast<double *>(ring + (size_t)nbuf * blk_bytes);               // [2][kChB][Q][RP]
-  uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * kChB * Q * RP);                  // [kChNbufMax]
+  unsigned char *halo_buf = reinterpret_cast<unsigned char *>(red + 2 * kChB * Q * RP);    // [kChHalo][512 U] (halo only)
+  uint64_t *full = reinterpret_cast<uint64_t *>(halo_buf + (halo ? kChHalo * 512 * U : 0)); // [kChNbufMax]
   uint64_t *empty = full + kChNbufMax;                                                     // [kChNbufMax]
   uint64_t *red_full = empty + kChNbufMax;                                                 // [2]
   uint64_t *red_empty = red_full + 2;                                                      // [2]
+  uint64_t *halo_full = red_empty + 2;                                                     // [kChHalo]
 
   const long long my_atoms = (long long)blockIdx.x < A ? (A - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int n_my = (int)my_atoms * split;  // atom-major items: all pieces of an atom are consecutive items of this CTA
@@ -317,6 +334,7 @@ __global__ void __launch_bounds__(kChThreads, 1)
       mbar_init(&red_full[i], kChS);
       mbar_init(&red_empty[i], nred);
     }
+    for (int i = 0; i < kChHalo; ++i) mbar_init(&halo_full[i], 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -431,6 +449,8 @@ __global__ void __launch_bounds__(kChThreads, 1)
       }
     const uint32_t col = 16u * (uint32_t)lane;  // column c of the lane: + 512 c
     int s = 0, ph = 0, g = 0;
+    const uint32_t halo_addr = smem_u32(halo_buf);
+    if (halo && warp == kChS - 1 && lane == 0) mbar_arrive(&halo_full[0]);  // (block 0 has no frame in front of it)
 
     // one block = kChSteps chain steps, history slots HALF * kChSteps + j (static)
     auto block = [&](auto half, const bool (&act)[U], const V (&m)[U], const int pitch) {
@@ -439,6 +459,7 @@ __global__ void __launch_bounds__(kChThreads, 1)
       const uint32_t prv = ring_addr + (uint32_t)(s == 0 ? nbuf - 1 : s - 1) * (uint32_t)blk_bytes;
       mbar_wait(&full[s], (uint32_t)ph);
       if (g >= 2) mbar_wait(&red_empty[g & 1], (uint32_t)(((g >> 1) - 1) & 1));
+      if (halo && warp == 0) mbar_wait(&halo_full[g % kChHalo], (uint32_t)((g / kChHalo) & 1));
       double *r = red + (size_t)(g & 1) * kChB * Q * RP;
       if constexpr (PD > 0) {
         // software pipeline over the kChSteps * U (step, column) tasks of the block: loads run PD columns ahead
@@ -479,12 +500,19 @@ __global__ void __launch_bounds__(kChThreads, 1)
         // ring-window partner: row fl + ov - w0 of this buffer, or of the previous one (w0 <= 25, ov = 0; the first
         // frames of an item read the previous item's last frames there: results for f < w0 are never used)
         const int pl = fl + ov - w0;
-        const uint32_t p_addr = pl >= 0 ? cur + (uint32_t)pl * (uint32_t)pitch : prv + (uint32_t)(pl + kChB) * (uint32_t)pitch;
+        uint32_t p_addr = pl >= 0 ? cur + (uint32_t)pl * (uint32_t)pitch : prv + (uint32_t)(pl + kChB) * (uint32_t)pitch;
+        uint32_t halo_st = 0;
+        if constexpr (J == 0) {  // (halo: w0 == 1) the frame in front of the block comes from chain 4's registers
+          if (halo && warp == 0) p_addr = halo_addr + (uint32_t)(g % kChHalo) * (512u * U);
+        }
+        if constexpr (J == kChSteps - 1) {
+          if (halo && warp == kChS - 1) halo_st = halo_addr + (uint32_t)((g + 1) % kChHalo) * (512u * U);
+        }
         double v[Q];
         if constexpr (sizeof(T) == 8)
-          ch_step_f64<HALF * kChSteps + J, U, NS, C1, C2, C3, Q>(x_addr, p_addr, col, act, m, h, v);
+          ch_step_f64<HALF * kChSteps + J, U, NS, C1, C2, C3, Q>(x_addr, p_addr, col, act, m, h, v, halo_st);
         else
-          ch_step_f32<HALF * kChSteps + J, U, NS, C1, C2, C3, Q>(x_addr, p_addr, col, act, m, h, v);
+          ch_step_f32<HALF * kChSteps + J, U, NS, C1, C2, C3, Q>(x_addr, p_addr, col, act, m, h, v, halo_st);
         if constexpr (SR) {
 #pragma unroll
           for (int q = 0; q < Q; ++q) r[(fl * Q + q) * kChRedPitch + lane] = v[q];
@@ -503,8 +531,9 @@ __global__ void __launch_bounds__(kChThreads, 1)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&red_full[g & 1]);
-        if (ov || NS == 0)
-          mbar_arrive(&empty[s]);  // (ov == w0, or no ring window at all: nothing of this buffer is needed again)
+        if (halo && warp == kChS - 1) mbar_arrive(&halo_full[(g + 1) % kChHalo]);
+        if (ov || NS == 0 || halo)
+          mbar_arrive(&empty[s]);  // (ov == w0, the halo, or no ring window at all: nothing of this buffer is needed again)
         else if (g >= 1)
           mbar_arrive(&empty[s == 0 ? nbuf - 1 : s - 1]);
       }
