@@ -156,15 +156,9 @@ __device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, co
   for (int q = 0; q < Q; ++q) s[q][0] = s[q][1] = 0.0;
 #pragma unroll
   for (int c = 0; c < U; ++c) {
-    const double2 xm = make_double2(x[c].x * m[c].x, x[c].y * m[c].y);
-    s[0][0] = fma(xm.x, x[c].x, s[0][0]);
-    s[0][1] = fma(xm.y, x[c].y, s[0][1]);
-    int q = 1;
-    if (NS) {
-      s[q][0] = fma(xm.x, p[c].x, s[q][0]);
-      s[q][1] = fma(xm.y, p[c].y, s[q][1]);
-      ++q;
-    }
+    // the history terms first (they need neither m * x nor the ring partner, and the oldest slot is read before it is
+    // overwritten), then m * x and the two sums that use it
+    int q = 1 + NS;
     if (C1) {
       const double2 y = h[(N + kChH - C1) % kChH][c];
       s[q][0] = fma(x[c].x, y.x, s[q][0]);
@@ -183,7 +177,14 @@ __device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, co
       s[q][1] = fma(x[c].y, y.y, s[q][1]);
       ++q;
     }
+    const double2 xm = make_double2(x[c].x * m[c].x, x[c].y * m[c].y);
     h[N][c] = xm;
+    s[0][0] = fma(xm.x, x[c].x, s[0][0]);
+    s[0][1] = fma(xm.y, x[c].y, s[0][1]);
+    if (NS) {
+      s[1][0] = fma(xm.x, p[c].x, s[1][0]);
+      s[1][1] = fma(xm.y, p[c].y, s[1][1]);
+    }
   }
 #pragma unroll
   for (int q = 0; q < Q; ++q) v[q] = s[q][0] + s[q][1];
