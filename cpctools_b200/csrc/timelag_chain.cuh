@@ -138,13 +138,15 @@ template <> struct ChVec<double> { using type = double2; };
 template <> struct ChVec<float> { using type = float4; };
 
 template <int N, int U, int NS, int C1, int C2, int C3, int Q>
-__device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, const uint32_t col, const bool (&act)[U],
+__device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, const uint32_t col, const uint32_t (&cofs)[U],
                                             const double2 (&m)[U], double2 (&h)[kChH][U], double (&v)[Q], const uint32_t halo_st = 0) {
+  // no predicates: a lane without a unit in column c reads the LAST unit of the piece instead (cofs) and multiplies it
+  // by m = 0 -- data of the same atom and frame, so a NaN there poisons nothing that is not NaN already
   double2 x[U], p[U];
 #pragma unroll
   for (int c = 0; c < U; ++c) {
-    x[c] = act[c] ? lds_d2(x_addr + col + 512u * c) : make_double2(0.0, 0.0);
-    if (NS) p[c] = act[c] ? lds_d2(p_addr + col + 512u * c) : make_double2(0.0, 0.0);
+    x[c] = lds_d2(x_addr + cofs[c]);
+    if (NS) p[c] = lds_d2(p_addr + cofs[c]);
   }
   if (halo_st) {  // the last frame of the block, for the first frame of the next one (chain 0)
 #pragma unroll
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(kChThreads, 1)
     if (halo && warp == kChS - 1 && lane == 0) mbar_arrive(&halo_full[0]);  // (block 0 has no frame in front of it)
 
     // one block = kChSteps chain steps, history slots HALF * kChSteps + j (static)
-    auto block = [&](auto half, const bool (&act)[U], const V (&m)[U], const int pitch) {
+    auto block = [&](auto half, const bool (&act)[U], const uint32_t (&cofs)[U], const V (&m)[U], const int pitch) {
       constexpr int HALF = decltype(half)::value;
       const uint32_t cur = ring_addr + (uint32_t)s * (uint32_t)blk_bytes;
       const uint32_t prv = ring_addr + (uint32_t)(s == 0 ? nbuf - 1 : s - 1) * (uint32_t)blk_bytes;
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(kChThreads, 1)
         }
         double v[Q];
         if constexpr (sizeof(T) == 8)
-          ch_step_f64<HALF * kChSteps + J, U, NS, C1, C2, C3, Q>(x_addr, p_addr, col, act, m, h, v, halo_st);
+          ch_step_f64<HALF * kChSteps + J, U, NS, C1, C2, C3, Q>(x_addr, p_addr, col, cofs, m, h, v, halo_st);
         else
           ch_step_f32<HALF * kChSteps + J, U, NS, C1, C2, C3, Q>(x_addr, p_addr, col, act, m, h, v, halo_st);
         if constexpr (SR) {
@@ -561,9 +563,12 @@ __global__ void __launch_bounds__(kChThreads, 1)
       // (the first block of an item reads its ring-window partners from the previous ITEM's last block with this
       // item's pitch: garbage either way, and never used)
       const int pitch = it.p == split - 1 ? pitch_last : pitch_full;
+      uint32_t cofs[U];  // byte offset of the lane's unit in column c (clamped to the last unit of the piece)
+#pragma unroll
+      for (int c = 0; c < U; ++c) cofs[c] = 16u * (uint32_t)min(lane + 32 * c, it.punits - 1);
       for (int b = 0; b < nblk; b += 2) {
-        block(std::integral_constant<int, 0>{}, act, m, pitch);
-        if (b + 1 < nblk) block(std::integral_constant<int, 1>{}, act, m, pitch);
+        block(std::integral_constant<int, 0>{}, act, cofs, m, pitch);
+        if (b + 1 < nblk) block(std::integral_constant<int, 1>{}, act, cofs, m, pitch);
       }
     }
   }
