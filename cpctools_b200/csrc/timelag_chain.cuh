@@ -153,9 +153,10 @@ __device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, co
     for (int c = 0; c < U; ++c)
       asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(halo_st + col + 512u * c), "d"(x[c].x), "d"(x[c].y) : "memory");
   }
-  double s[Q][2];
+  // ONE chain per sum: the Q sums are Q independent chains already (a second chain per sum costs 10 registers and 5
+  // additions per step)
 #pragma unroll
-  for (int q = 0; q < Q; ++q) s[q][0] = s[q][1] = 0.0;
+  for (int q = 0; q < Q; ++q) v[q] = 0.0;
 #pragma unroll
   for (int c = 0; c < U; ++c) {
     // the history terms first (they need neither m * x nor the ring partner, and the oldest slot is read before it is
@@ -163,33 +164,24 @@ __device__ __forceinline__ void ch_step_f64(uint32_t x_addr, uint32_t p_addr, co
     int q = 1 + NS;
     if (C1) {
       const double2 y = h[(N + kChH - C1) % kChH][c];
-      s[q][0] = fma(x[c].x, y.x, s[q][0]);
-      s[q][1] = fma(x[c].y, y.y, s[q][1]);
+      v[q] = fma(x[c].y, y.y, fma(x[c].x, y.x, v[q]));
       ++q;
     }
     if (C2) {
       const double2 y = h[(N + kChH - C2) % kChH][c];
-      s[q][0] = fma(x[c].x, y.x, s[q][0]);
-      s[q][1] = fma(x[c].y, y.y, s[q][1]);
+      v[q] = fma(x[c].y, y.y, fma(x[c].x, y.x, v[q]));
       ++q;
     }
     if (C3) {
       const double2 y = h[(N + kChH - C3) % kChH][c];
-      s[q][0] = fma(x[c].x, y.x, s[q][0]);
-      s[q][1] = fma(x[c].y, y.y, s[q][1]);
+      v[q] = fma(x[c].y, y.y, fma(x[c].x, y.x, v[q]));
       ++q;
     }
     const double2 xm = make_double2(x[c].x * m[c].x, x[c].y * m[c].y);
     h[N][c] = xm;
-    s[0][0] = fma(xm.x, x[c].x, s[0][0]);
-    s[0][1] = fma(xm.y, x[c].y, s[0][1]);
-    if (NS) {
-      s[1][0] = fma(xm.x, p[c].x, s[1][0]);
-      s[1][1] = fma(xm.y, p[c].y, s[1][1]);
-    }
+    v[0] = fma(xm.y, x[c].y, fma(xm.x, x[c].x, v[0]));
+    if (NS) v[1] = fma(xm.y, p[c].y, fma(xm.x, p[c].x, v[1]));
   }
-#pragma unroll
-  for (int q = 0; q < Q; ++q) v[q] = s[q][0] + s[q][1];
 }
 
 // fp32 data: products and two 2U-term chains per sum in fp32, promoted to double before the cross-lane sum (the same
