@@ -10,17 +10,26 @@
 //   * lane l owns the units l, l + 32, ... (U of them, 16 bytes each) of the piece and keeps m * x of the last TEN
 //     chain frames of those units in registers: the partners for windows 5c (c = 1..10) are register operands;
 //   * only the remaining window (1 in the headline sweep) is read from the ring, which therefore holds just the
-//     landing blocks of the TMA engine (4 x 25 frames) instead of a 50-frame history: a piece is up to 128 units
-//     (5 pieces per 9.8 kB row instead of 6) and every 128-bit load of a warp is one contiguous 512-byte row segment
-//     (conflict free whatever the pitch).
-// The price is a cross-lane sum: a lane ends a frame with Q partial sums over ITS units; the warp adds them with a
-// transposing butterfly (3 + 2 + 1 + 1 + 1 64-bit shuffles for Q = 5, fixed order -> bitwise reproducible).
-// Per 512 B of HBM data: 4 (own frame) + 4 (window 1) + 4 (16 shuffles per 4 units) + 4 (TMA write) = 16 cycles.
+//     landing blocks of the TMA engine (3 x 25 frames) instead of a 50-frame history: a piece is 128 units = 2 KB
+//     (5 pieces per 9.8 kB row instead of 6, cut at multiples of 2 KB from the row start, the narrower last piece with
+//     its own tensor map) and every 128-bit load of a warp is one contiguous 512-byte row segment (conflict free
+//     whatever the pitch);
+//   * nothing of a block is held back for the next one: the window-1 partner of a block's first frame is the LAST frame
+//     of the block before, which chain 4's warp holds in registers and hands to chain 0 through a small shared-memory
+//     halo (other ring windows <= 2: the boxes overlap by that many rows; 3..25: the previous buffer is kept).
+// The price is a cross-lane sum: a lane ends a frame with Q partial sums over ITS units.  They go through shared memory
+// (red[frame][sum][lane]) to two reducer warps, which add the 32 lanes in a fixed tree and then the pieces of the atom
+// (bitwise reproducible across grid sizes and atom counts).  A shuffle butterfly inside the consumer warps (ch_reduce,
+// SR = false: kept, not instantiated) was 2x slower: with 255 registers per thread only five consumer warps fit, one
+// per scheduler, and a lone warp cannot hide five dependent shuffle + add levels.
+// Per 512 B of HBM data: 4 (own frame) + 4 (window 1) + 2.5 + 2.5 (partial sums) + 4 (TMA write) = 17 shared-memory
+// cycles against 26.55.  Measured: 0.96-0.99 of the HBM copy peak alone, 0.86-0.89 sustained under the
+// power cap, against 0.78 / 0.72-0.75 for timelag_kernel.
 // The history index must be static (registers cannot be indexed): the frame loop is unrolled over 10 chain steps
 // = 2 blocks of 25 frames.
-// Applies to: TMA-able rows of whole units, cosine-type kinds, >= 4 atoms per SM (atom-major items), windows =
-// up to one window <= 25 that is no multiple of 5 (or is beyond 50) + up to three distinct multiples of 5 up to 50,
-// in one of the instantiated patterns (chain_choose).  Everything else takes timelag_kernel / timelag_pair_kernel.
+// Applies to: TMA-able rows of whole units, cosine-type kinds, atom counts that fill the SMs (a CTA owns whole atoms),
+// windows = up to one window <= 25 that is no multiple of 5 + up to three distinct multiples of 5 up to 50, in one of
+// the instantiated patterns (chain_choose).  Everything else takes timelag_kernel / timelag_pair_kernel.
 #pragma once
 
 namespace soapb {
@@ -29,7 +38,7 @@ constexpr int kChS = 5;      // chain stride in frames == consumer warps
 constexpr int kChH = 10;     // chain steps of history in registers (windows up to 50)
 constexpr int kChSteps = 5;  // chain steps per block
 constexpr int kChB = kChS * kChSteps;  // frames per block (25)
-constexpr int kChNbufMax = 4;  // ring blocks: previous (window-1 partner of a block's first frames), current, 1-2 in flight
+constexpr int kChNbufMax = 4;  // ring blocks (as many as fit, at least 3: current + in flight, + the previous one for ring windows 3..25)
 constexpr int kChRed = 2;     // reducer warps in the CTA (the launch decides how many of them work: nred)
 constexpr int kChThreads = (kChS + 1 + kChRed) * 32;
 constexpr int kChRedPitch = 34;  // doubles per (frame, sum) row of the lanes' partial sums (32 + 2: conflict-free 128-bit reads)
