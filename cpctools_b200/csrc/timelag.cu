@@ -33,6 +33,7 @@ namespace soapb {
 
 constexpr int kBlk = 32;     // frames per block == lanes per warp
 constexpr int kTlWarps = 8;  // consumer warps (two per SM sub-partition)
+constexpr int kChainAlignDefault = 1;  // SOAP_TL_CHAIN_ALIGN default: on (+1.4 % where the kernel is HBM bound, level where it is SM bound)
 constexpr int kChainHaloDefault = 1;  // SOAP_TL_CHAIN_HALO default: on (3-5 % faster than overlapping boxes, interleaved A/B)
 constexpr int kChainDefault = -1;  // SOAP_TL_CHAIN default (timelag_chain.cuh): -1 = float64 data only (measured)
 constexpr int kPairDefault = -1;  // SOAP_TL_PAIR default (timelag_pair.cuh): -1 = float32 data only (measured)
@@ -949,17 +950,35 @@ static int launch_timelag_chain(const void *X, const void *mult, double *scratch
   SOAP_REQUIRE(row_words < 2147483647LL, "soap_timelag: a frame of %lld bytes exceeds the tensor-map coordinate range", (long long)row_words * 8);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  CUtensorMap tmap_last;
+  CUtensorMap tmap_last, tmap_first, tmap_last4;
   memset(&tmap_last, 0, sizeof(tmap_last));
+  memset(&tmap_first, 0, sizeof(tmap_first));
+  memset(&tmap_last4, 0, sizeof(tmap_last4));
+  // SOAP_TL_CHAIN_ALIGN=1: rows of 8 k + 4 units (every other atom starts 64 bytes into a 128-byte line): that atom's
+  // pieces are cut 4 units early, so that every boundary inside a row falls on a line (ch_item)
+  const int n_units = D / (16 / (int)sizeof(T));
+  const int align = (env_int("SOAP_TL_CHAIN_ALIGN", kChainAlignDefault) != 0 && pl.split > 1 && (n_units & 7) == 4 &&
+                     (reinterpret_cast<uintptr_t>(X) & 127) == 0 && pl.last_units + 4 <= pl.upp)
+                        ? 1 : 0;
   int rc = make_tensor_map_2d(&tmap, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, pl.pitch / 8, kChB + ov, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_NONE);
   if (rc) return rc;
   rc = make_tensor_map_2d(&tmap_last, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, pl.last_units * 2, kChB + ov, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE);
   if (rc) return rc;
+  if (align) {
+    rc = make_tensor_map_2d(&tmap_first, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, (pl.upp - 4) * 2, kChB + ov, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tmap_last4, X, CU_TENSOR_MAP_DATA_TYPE_UINT64, 8, F, row_words, (pl.last_units + 4) * 2, kChB + ov, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+  }
+  const int4 pitch4 = make_int4(pl.pitch, (pl.upp - 4) * 16, pl.last_units * 16, (pl.last_units + 4) * 16);
   ProfScope prof(SOAP_PROF_TIMELAG, s);
   kern<<<(unsigned)grid, kChThreads, pl.smem, s>>>(static_cast<const T *>(mult), scratch, cta_acc, (long long)F, (long long)A, D, pl.split, pl.upp,
-                                                   pl.pitch, pl.last_units * 16, (int)pl.blk_bytes, pl.nbuf, ch.w0, ov, env_int("SOAP_TL_CHAIN_RED", 2) == 1 ? 1 : 2, halo, tmap, tmap_last);
+                                                   pitch4, (int)pl.blk_bytes, pl.nbuf, ch.w0, ov, env_int("SOAP_TL_CHAIN_RED", 2) == 1 ? 1 : 2, halo, align, tmap,
+                                                   tmap_first, tmap_last, tmap_last4);
   g_tl_last_kernel = "timelag_chain_kernel";
   return check_launch("timelag_chain_kernel");
 }

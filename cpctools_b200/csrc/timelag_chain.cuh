@@ -294,6 +294,37 @@ __device__ __forceinline__ void ch_static_for(F &&f, std::integer_sequence<int, 
   (f(std::integral_constant<int, I>{}), ...);
 }
 
+// Item of the chain kernel.  `align` (rows that start 64 bytes into a 128-byte line for every other atom: n_units % 8
+// == 4): the pieces of such an atom are cut at p * upp - 4 units, so that every piece boundary inside a row falls on a
+// 128-byte line; its first piece is 4 units shorter, its last one 4 units longer.  kind: 0 full piece, 1 the short
+// first piece, 2 the last piece, 3 the long last piece (tensor map / pitch of the box).
+struct ChItem {
+  TlItem it;
+  int kind;
+};
+template <int UE>
+__device__ __forceinline__ ChItem ch_item(int k, int split, int upp, int D, int align) {
+  ChItem ci;
+  ci.it = tl_item<UE>(k, split, upp, D, true, false);
+  const bool last = ci.it.p == split - 1;
+  ci.kind = last ? 2 : 0;
+  if (align) {
+    const int n_units = D / UE;
+    const int s4 = (int)((ci.it.a * n_units) & 7);  // 0 or 4
+    if (s4) {
+      const int u0 = ci.it.p == 0 ? 0 : ci.it.p * upp - s4;
+      const int u1 = last ? n_units : (ci.it.p + 1) * upp - s4;
+      constexpr int ES = 16 / UE;
+      ci.it.e0 = u0 * UE;
+      ci.it.punits = u1 - u0;
+      ci.it.pe = ci.it.punits * UE;
+      ci.it.w0 = (ci.it.a * D + ci.it.e0) * ES / 8;
+      ci.kind = last ? 3 : (ci.it.p == 0 ? 1 : 0);
+    }
+  }
+  return ci;
+}
+
 // Warp roles: warps 0..4 consume (warp = frame mod 5, lane = units), warp 5 produces (one tensor-map box of 25 frames
 // x one piece per block), warps 6 and 7 add the lanes' partial sums and the pieces of an atom (L2-resident per-CTA
 // accumulator, as timelag_kernel); with one reducer warp it was 81 % busy and the consumers waited for it 10 % of
@@ -307,8 +338,9 @@ __device__ __forceinline__ void ch_static_for(F &&f, std::integer_sequence<int, 
 template <typename T, int U, int NS, int C1, int C2, int C3, bool HAS_MULT, bool SR, int PD>
 __global__ void __launch_bounds__(kChThreads, 1)
     timelag_chain_kernel(const T *__restrict__ mult, double *__restrict__ sums, double *__restrict__ cta_acc, long long F, long long A,
-                         int D, int split, int upp, int pitch_full, int pitch_last, int blk_bytes, int nbuf, int w0, int ov, int nred, int halo,
-                         const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_last) {
+                         int D, int split, int upp, int4 pitch4, int blk_bytes, int nbuf, int w0, int ov, int nred, int halo, int align,
+                         const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_first,
+                         const __grid_constant__ CUtensorMap tmap_last, const __grid_constant__ CUtensorMap tmap_last4) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using V = typename ChVec<T>::type;
   constexpr int UE = 16 / (int)sizeof(T);
@@ -347,15 +379,17 @@ __global__ void __launch_bounds__(kChThreads, 1)
     // ===== producer: block g goes to buffer g % nbuf, free once block g - nbuf + 1 is consumed =======================
     int s = 0, ph = 0, g = 0;
     for (int k = 0; k < n_my; ++k) {
-      const TlItem it = tl_item<UE>(k, split, upp, D, true, false);
-      const bool last = it.p == split - 1;
+      const ChItem ci = ch_item<UE>(k, split, upp, D, align);
+      const TlItem &it = ci.it;
+      const int box_pitch = ci.kind == 0 ? pitch4.x : ci.kind == 1 ? pitch4.y : ci.kind == 2 ? pitch4.z : pitch4.w;
+      const CUtensorMap *box_map = ci.kind == 0 ? &tmap : ci.kind == 1 ? &tmap_first : ci.kind == 2 ? &tmap_last : &tmap_last4;
       for (int b = 0; b < nblk; ++b, ++g) {
         if (g >= nbuf) mbar_wait(&empty[s], (uint32_t)(ph ^ 1));
         if (lane == 0) {
           // rows beyond F are zero-filled and still counted in the transaction bytes
           // (and so are the rows -ov .. -1 in front of an item's first block)
-          mbar_expect_tx(&full[s], (uint32_t)(kChB + ov) * (uint32_t)(last ? pitch_last : pitch_full));
-          tma_load_2d(ring + (size_t)s * blk_bytes, last ? &tmap_last : &tmap, (int)it.w0, b * kChB - ov, &full[s]);
+          mbar_expect_tx(&full[s], (uint32_t)(kChB + ov) * (uint32_t)box_pitch);
+          tma_load_2d(ring + (size_t)s * blk_bytes, box_map, (int)it.w0, b * kChB - ov, &full[s]);
         }
         if (++s == nbuf) s = 0, ph ^= 1;
       }
@@ -546,7 +580,8 @@ __global__ void __launch_bounds__(kChThreads, 1)
     };
 
     for (int k = 0; k < n_my; ++k) {
-      const TlItem it = tl_item<UE>(k, split, upp, D, true, false);
+      const ChItem ci = ch_item<UE>(k, split, upp, D, align);
+      const TlItem &it = ci.it;
       bool act[U];
       V m[U];
 #pragma unroll
@@ -563,7 +598,7 @@ __global__ void __launch_bounds__(kChThreads, 1)
       }
       // (the first block of an item reads its ring-window partners from the previous ITEM's last block with this
       // item's pitch: garbage either way, and never used)
-      const int pitch = it.p == split - 1 ? pitch_last : pitch_full;
+      const int pitch = ci.kind == 0 ? pitch4.x : ci.kind == 1 ? pitch4.y : ci.kind == 2 ? pitch4.z : pitch4.w;
       uint32_t cofs[U];  // byte offset of the lane's unit in column c (clamped to the last unit of the piece)
 #pragma unroll
       for (int c = 0; c < U; ++c) cofs[c] = 16u * (uint32_t)min(lane + 32 * c, it.punits - 1);

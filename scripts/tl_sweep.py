@@ -40,7 +40,7 @@ def run():
     return sum(ms) / len(ms)
 
 
-KNOBS = ("SOAP_TL_CHAIN", "SOAP_TL_CHAIN_HALO", "SOAP_TL_CHAIN_BAL", "SOAP_TL_CHAIN_FAST", "SOAP_TL_CHAIN_RED", "SOAP_TL_CHAIN_OV", "SOAP_TL_CHAIN_U", "SOAP_TL_CHAIN_SR", "SOAP_TL_PAIR", "SOAP_TL_PAIR_UB", "SOAP_TL_WARPS", "SOAP_TL_SPLIT", "SOAP_TL_AHEAD", "SOAP_TL_DIAG", "SOAP_TL_GRID", "SOAP_TL_RB", "SOAP_RB_LINES", "SOAP_RB_STAGES", "SOAP_RB_DIAG")
+KNOBS = ("SOAP_TL_CHAIN", "SOAP_TL_CHAIN_ALIGN", "SOAP_TL_CHAIN_HALO", "SOAP_TL_CHAIN_BAL", "SOAP_TL_CHAIN_FAST", "SOAP_TL_CHAIN_RED", "SOAP_TL_CHAIN_OV", "SOAP_TL_CHAIN_U", "SOAP_TL_CHAIN_SR", "SOAP_TL_PAIR", "SOAP_TL_PAIR_UB", "SOAP_TL_WARPS", "SOAP_TL_SPLIT", "SOAP_TL_AHEAD", "SOAP_TL_DIAG", "SOAP_TL_GRID", "SOAP_TL_RB", "SOAP_RB_LINES", "SOAP_RB_STAGES", "SOAP_RB_DIAG")
 for cfg in sys.argv[1:] or [""]:
     for k in KNOBS:
         os.environ.pop(k, None)
